@@ -1,0 +1,66 @@
+// One translation unit per bra class (JQC_LI >= JQC_LJ), compiled with -DJQC_LI=.. -DJQC_LJ=..
+// Instantiates the J/K kernels for every ket class lk <= li, ll <= lk and the three
+// (do_j, do_k) variants, and exports one launcher.  (The reference JIT-compiles the same
+// specialisations at run time through NVRTC: jqc/backend/jk.py:56-115.)
+#include "jk_1q1t.cuh"
+#include "jk_launch.h"
+
+namespace jqc {
+
+template <int LK, int LL, bool DO_J, bool DO_K>
+static cudaError_t launch_one(const JKArgs& a, int nsm, cudaStream_t st)
+{
+    using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
+    constexpr bool SMALL = S::N <= JQC_SMALL_N;
+    constexpr int NT = SMALL ? 256 : 128;
+    void (*kern)(const JKArgs);
+    if constexpr (SMALL) kern = jk_1q1t_kernel_small<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
+    else kern = jk_1q1t_kernel_large<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, 0);
+        if (e != cudaSuccess) return e;
+        blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    kern<<<nsm * blocks_per_sm, NT, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int LK, int LL>
+static cudaError_t launch_variant(int variant, const JKArgs& a, int nsm, cudaStream_t st)
+{
+    switch (variant) {
+        case 3: return launch_one<LK, LL, true, true>(a, nsm, st);
+        case 1: return launch_one<LK, LL, true, false>(a, nsm, st);
+        case 2: return launch_one<LK, LL, false, true>(a, nsm, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+#define JQC_CAT_(a, b, c) a##b##_##c
+#define JQC_CAT(a, b, c) JQC_CAT_(a, b, c)
+
+// (templated on a dummy so that the discarded `if constexpr` branches are not instantiated)
+template <int Z>
+static cudaError_t dispatch(int lk, int ll, int variant, const JKArgs& a, int nsm, cudaStream_t st)
+{
+#define CASE(K, L)                                                       \
+    if constexpr (K + Z <= JQC_LI && L <= K) {                           \
+        if (lk == K && ll == L) return launch_variant<K, L>(variant, a, nsm, st); \
+    }
+    CASE(0, 0)
+    CASE(1, 0) CASE(1, 1)
+    CASE(2, 0) CASE(2, 1) CASE(2, 2)
+    CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)
+    CASE(4, 0) CASE(4, 1) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+#undef CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t JQC_CAT(jk_launch_, JQC_LI, JQC_LJ)(int lk, int ll, int variant, const JKArgs& a, int nsm, cudaStream_t st)
+{
+    return dispatch<0>(lk, ll, variant, a, nsm, st);
+}
+
+}  // namespace jqc

@@ -1,0 +1,28 @@
+// Launcher table shared by engine.cu and the per-class translation units (jk_inst.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace jqc {
+struct JKArgs;
+#define JQC_DECL(I, J) cudaError_t jk_launch_##I##_##J(int lk, int ll, int variant, const JKArgs& a, int nsm, cudaStream_t st);
+JQC_DECL(0, 0)
+JQC_DECL(1, 0) JQC_DECL(1, 1)
+JQC_DECL(2, 0) JQC_DECL(2, 1) JQC_DECL(2, 2)
+JQC_DECL(3, 0) JQC_DECL(3, 1) JQC_DECL(3, 2) JQC_DECL(3, 3)
+JQC_DECL(4, 0) JQC_DECL(4, 1) JQC_DECL(4, 2) JQC_DECL(4, 3) JQC_DECL(4, 4)
+#undef JQC_DECL
+
+// variant: bit0 = J, bit1 = K.  Requires li >= lj, li >= lk, lk >= ll (the order in which the
+// group-quartet loop of the reference enumerates classes, jqc/pyscf/jk.py:145-151).
+inline cudaError_t jk_launch(int li, int lj, int lk, int ll, int variant, const JKArgs& a, int nsm, cudaStream_t st)
+{
+#define JQC_CALL(I, J) if (li == I && lj == J) return jk_launch_##I##_##J(lk, ll, variant, a, nsm, st);
+    JQC_CALL(0, 0)
+    JQC_CALL(1, 0) JQC_CALL(1, 1)
+    JQC_CALL(2, 0) JQC_CALL(2, 1) JQC_CALL(2, 2)
+    JQC_CALL(3, 0) JQC_CALL(3, 1) JQC_CALL(3, 2) JQC_CALL(3, 3)
+    JQC_CALL(4, 0) JQC_CALL(4, 1) JQC_CALL(4, 2) JQC_CALL(4, 3) JQC_CALL(4, 4)
+#undef JQC_CALL
+    return cudaErrorInvalidValue;
+}
+}  // namespace jqc
