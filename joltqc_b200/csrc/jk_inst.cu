@@ -2,15 +2,51 @@
 // Instantiates the J/K kernels for every ket class lk <= li, ll <= lk and the three
 // (do_j, do_k) variants, and exports one launcher.  (The reference JIT-compiles the same
 // specialisations at run time through NVRTC: jqc/backend/jk.py:56-115.)
-#include "jk_1q1t.cuh"
+#include "jk_warp.cuh"
 #include "jk_launch.h"
 
 namespace jqc {
+
+// Multi-lane kernel: warps per block chosen so that two blocks fit the 227 KB of an SM when possible.
+template <int LK, int LL>
+struct WarpCfg {
+    using P = WarpPlan<JQC_LI, JQC_LJ, LK, LL>;
+    static constexpr size_t WARP_BYTES = (size_t)P::QPW * P::PER_GROUP * sizeof(double);
+    static constexpr int nwarps()
+    {
+        int n = (int)(100 * 1024 / WARP_BYTES);
+        return n > 8 ? 8 : (n < 1 ? 1 : n);
+    }
+    static constexpr int NWARPS = nwarps();
+    static constexpr size_t SMEM = WARP_BYTES * NWARPS;
+    static constexpr bool FITS = SMEM <= 200 * 1024;
+};
+
+template <int LK, int LL, bool DO_J, bool DO_K>
+static cudaError_t launch_warp(const JKArgs& a, int nsm, cudaStream_t st)
+{
+    using C = WarpCfg<LK, LL>;
+    auto kern = jk_warp_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, C::NWARPS>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::NWARPS * 32, C::SMEM);
+        if (e != cudaSuccess) return e;
+        blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    kern<<<nsm * blocks_per_sm, C::NWARPS * 32, C::SMEM, st>>>(a);
+    return cudaGetLastError();
+}
 
 template <int LK, int LL, bool DO_J, bool DO_K>
 static cudaError_t launch_one(const JKArgs& a, int nsm, cudaStream_t st)
 {
     using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
+    if constexpr (S::N > JQC_SMALL_N && WarpCfg<LK, LL>::FITS && JQC_LI <= 3) {
+        return launch_warp<LK, LL, DO_J, DO_K>(a, nsm, st);
+    }
     constexpr bool SMALL = S::N <= JQC_SMALL_N;
     constexpr int NT = SMALL ? 256 : 128;
     void (*kern)(const JKArgs);
