@@ -56,8 +56,11 @@ __device__ __forceinline__ void fill_g_dir(double* __restrict__ gd, const double
                                            const double b10, const double b01, const double b00, const double ab,
                                            const double cd)
 {
+    // shared-memory strides: DK padded to an odd number of doubles so that the (k,l) slots that
+    // different lanes read in the product phase fall into different banks; DL keeps the exact
+    // (LK+1)*DK aliasing the in-place HRR relies on.
     using S = QuartetShape<LI, LJ, LK, LL>;
-    constexpr int DJ = S::DJ, DK = S::DK, DL = S::DL, LIJ = S::LIJ, LKL = S::LKL;
+    constexpr int DJ = S::DJ, DK = S::DK | 1, DL = DK * (LK + 1), LIJ = S::LIJ, LKL = S::LKL;
     gd[0] = seed;
     if constexpr (LIJ > 0) {
         double s0 = seed, s1 = c0 * seed;
@@ -100,7 +103,7 @@ __device__ __forceinline__ void fill_g_dir(double* __restrict__ gd, const double
     }
     if constexpr (LL > 0) {
 #pragma unroll
-        for (int ij = 0; ij < DK; ij++)
+        for (int ij = 0; ij < S::DK; ij++)
 #pragma unroll
             for (int l = 0; l < LL; l++)
 #pragma unroll
@@ -143,7 +146,9 @@ struct WarpPlan {
     static constexpr int T = lanes();
     static constexpr int QPW = 32 / T;
     static constexpr int NKLP = (NKL + T - 1) / T;
-    static constexpr int G_ALL = S::NROOTS * 3 * S::GSIZE;
+    static constexpr int DKP = S::DK | 1, DLP = DKP * (LK + 1), GSP = DLP * (LL + 1);
+    static constexpr int IS = GSP | 1;                  // stride between (root, direction) arrays: odd
+    static constexpr int G_ALL = S::NROOTS * 3 * IS;
     static constexpr int NDBLK = NIJ + NKL + S::NFJ * S::NFL + S::NFJ * S::NFK + S::NFI * S::NFL + S::NFI * S::NFK;
     static constexpr int STAGE = 2 * NKL * (S::NFI + S::NFJ) + T * NIJ;
     // shared-memory doubles per quartet group: [rw][g of all roots][D blocks][staging].  With a
@@ -153,7 +158,7 @@ struct WarpPlan {
     static constexpr int OFF_D = OFF_G + (ALIAS ? (G_ALL > STAGE ? G_ALL : STAGE) : G_ALL);
     static constexpr int OFF_STAGE = ALIAS ? OFF_G : OFF_D + NDBLK;
     static constexpr int END = ALIAS ? OFF_D + NDBLK : OFF_STAGE + STAGE;
-    static constexpr int PER_GROUP = ((END + 1) / 2) * 2 + 2;   // even, +2 pad against bank aliasing
+    static constexpr int PER_GROUP = END | 1;            // odd stride between quartet groups
 };
 
 template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K, int NWARPS>
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(NWARPS * 32) jk_warp_kernel(const JKArgs a)
     using S = QuartetShape<LI, LJ, LK, LL>;
     using P = WarpPlan<LI, LJ, LK, LL>;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL;
-    constexpr int NROOTS = S::NROOTS, GS = S::GSIZE, DJ = S::DJ, DK = S::DK, DL = S::DL;
+    constexpr int NROOTS = S::NROOTS, GS = P::IS, DJ = S::DJ, DK = P::DKP, DL = P::DLP;
     constexpr int T = P::T, QPW = P::QPW, NKLP = P::NKLP, NKL = P::NKL, NPASS = P::NPASS, NJC = P::NJC;
     constexpr int NIJ = P::NIJ;
 
