@@ -14,8 +14,10 @@ struct WarpCfg {
     static constexpr size_t WARP_BYTES = (size_t)P::QPW * P::PER_GROUP * sizeof(double);
     static constexpr int nwarps()
     {
-        int n = (int)(100 * 1024 / WARP_BYTES);
-        return n > 8 ? 8 : (n < 1 ? 1 : n);
+        // blocks of <= 4 warps, small enough that shared memory allows >= 16 warps per SM when the
+        // per-warp footprint permits
+        int n = (int)(56 * 1024 / WARP_BYTES);
+        return n > 4 ? 4 : (n < 1 ? 1 : n);
     }
     static constexpr int NWARPS = nwarps();
     static constexpr size_t SMEM = WARP_BYTES * NWARPS;

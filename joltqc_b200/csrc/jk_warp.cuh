@@ -161,8 +161,11 @@ struct WarpPlan {
     static constexpr int PER_GROUP = END | 1;            // odd stride between quartet groups
 };
 
+#ifndef JQC_WARP_REGS
+#define JQC_WARP_REGS 128   // register budget per thread of the multi-lane kernel (occupancy lever)
+#endif
 template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32) jk_warp_kernel(const JKArgs a)
+__global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS * 32)) jk_warp_kernel(const JKArgs a)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     using P = WarpPlan<LI, LJ, LK, LL>;
