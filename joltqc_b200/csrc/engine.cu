@@ -92,6 +92,7 @@ struct jqc_engine {
     DevBuf<int> d_logmax, d_nact;
     DevBuf<ushort4> d_queue;
     DevBuf<unsigned> d_counters;
+    DevBuf<unsigned long long> d_qcounts;
     int rank = 0, world = 1;
     // state of the last build
     int last_n = 0, last_neff = 0, last_hermi = 1, last_j = 0, last_k = 0, launches = 0;
@@ -214,6 +215,7 @@ extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine
     CU(e->d_logmax.ensure(1));
     CU(e->d_nact.ensure(e->npairs()));
     CU(e->d_counters.ensure(MAX_CHUNKS));
+    CU(e->d_qcounts.ensure(MAX_CHUNKS));
     *out = e.release();
     return JQC_OK;
 }
@@ -395,6 +397,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(e->d_vjk.p, 0, 2 * neff * nao2 * sizeof(double), st));
     CU(cudaMemsetAsync(e->d_counters.p, 0, MAX_CHUNKS * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(e->d_qcounts.p, 0, MAX_CHUNKS * sizeof(unsigned long long), st));
     // The only host round trip of a build: the per-group-pair active tile counts (a few hundred
     // ints) so that no empty chunk is ever launched.  It happens before any heavy kernel is
     // enqueued, i.e. with an empty pipeline (the reference syncs here too, jk.py:183).
@@ -452,6 +455,8 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             s.do_k = with_k;
             s.queue = e->d_queue.p;
             s.counter = e->d_counters.p + cid;
+            s.qcount = e->d_qcounts.p + cid;
+            s.tile_mode = jk_uses_tiles(li, lj, lk, ll) ? 1 : 0;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (e->profiling) {
                 while (e->ev.size() < nev + 2) { cudaEvent_t x; CU(cudaEventCreate(&x)); e->ev.push_back(x); }
@@ -547,8 +552,8 @@ extern "C" int jqc_last_stats(jqc_engine* e, long long* counts, long long* prim_
     if (!e->built) return fail(JQC_ESTATE, "no build yet");
     CU(cudaSetDevice(e->device));
     CU(cudaDeviceSynchronize());
-    std::vector<unsigned> h(e->chunks.size());
-    if (!h.empty()) CU(cudaMemcpy(h.data(), e->d_counters.p, h.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> h(e->chunks.size());
+    if (!h.empty()) CU(cudaMemcpy(h.data(), e->d_qcounts.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (counts) std::memset(counts, 0, 625 * sizeof(long long));
     if (prim_weighted) std::memset(prim_weighted, 0, 625 * sizeof(long long));
     std::fill(e->class_ms.begin(), e->class_ms.end(), 0.f);

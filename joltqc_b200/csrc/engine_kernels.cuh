@@ -112,7 +112,9 @@ struct ScreenArgs {
     float cutoff;                        // log(cutoff_fp32): evaluate above this
     int do_j, do_k;
     ushort4* __restrict__ queue;
-    unsigned* __restrict__ counter;
+    unsigned* __restrict__ counter;          // queue entries written by this chunk
+    unsigned long long* __restrict__ qcount; // quartets that passed (accounting)
+    int tile_mode;                           // 1: emit (i, j, k-tile, l-tile, mask16) records for jk_tile16
 };
 
 // Thread = (one (i,j) shell pair of an ij tile) x (one kl tile): 16 quartet tests in the
@@ -191,6 +193,20 @@ __global__ void __launch_bounds__(256) screen_tasks_kernel(const ScreenArgs s)
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     if (total == 0) return;
+    if (lane == 31) atomicAdd(s.qcount, (unsigned long long)total);
+    if (s.tile_mode) {
+        // one 16-byte record per thread with survivors
+        const unsigned has = __ballot_sync(0xffffffffu, mask != 0);
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(s.counter, (unsigned)__popc(has));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (mask) {
+            uint4* q = reinterpret_cast<uint4*>(s.queue);
+            q[base + __popc(has & ((1u << lane) - 1u))] =
+                make_uint4((unsigned)ish | ((unsigned)jsh << 16), (unsigned)tk | ((unsigned)tl << 16), mask, 0u);
+        }
+        return;
+    }
     unsigned base = 0;
     if (lane == 31) base = atomicAdd(s.counter, (unsigned)total);
     base = __shfl_sync(0xffffffffu, base, 31);

@@ -2,6 +2,7 @@
 // Instantiates the J/K kernels for every ket class lk <= li, ll <= lk and the three
 // (do_j, do_k) variants, and exports one launcher.  (The reference JIT-compiles the same
 // specialisations at run time through NVRTC: jqc/backend/jk.py:56-115.)
+#include "jk_tile16.cuh"
 #include "jk_warp.cuh"
 #include "jk_launch.h"
 
@@ -51,8 +52,9 @@ static cudaError_t launch_one(const JKArgs& a, int nsm, cudaStream_t st)
     }
     constexpr bool SMALL = S::N <= JQC_SMALL_N;
     constexpr int NT = SMALL ? 256 : 128;
+    static_assert(JQC_SMALL_N == 81, "keep jk_uses_tiles() in jk_launch.h in sync");
     void (*kern)(const JKArgs);
-    if constexpr (SMALL) kern = jk_1q1t_kernel_small<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
+    if constexpr (SMALL) kern = jk_tile16_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
     else kern = jk_1q1t_kernel_large<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {

@@ -12,6 +12,14 @@ JQC_DECL(3, 0) JQC_DECL(3, 1) JQC_DECL(3, 2) JQC_DECL(3, 3)
 JQC_DECL(4, 0) JQC_DECL(4, 1) JQC_DECL(4, 2) JQC_DECL(4, 3) JQC_DECL(4, 4)
 #undef JQC_DECL
 
+// Classes whose blocks fit in one thread's registers are fed (i, j, k-tile, l-tile, mask) records
+// (jk_tile16.cuh); everything else consumes flat ushort4 quartet lists.
+inline bool jk_uses_tiles(int li, int lj, int lk, int ll)
+{
+    auto nf = [](int l) { return (l + 1) * (l + 2) / 2; };
+    return nf(li) * nf(lj) * nf(lk) * nf(ll) <= 81;
+}
+
 // variant: bit0 = J, bit1 = K.  Requires li >= lj, li >= lk, lk >= ll (the order in which the
 // group-quartet loop of the reference enumerates classes, jqc/pyscf/jk.py:145-151).
 inline cudaError_t jk_launch(int li, int lj, int lk, int ll, int variant, const JKArgs& a, int nsm, cudaStream_t st)

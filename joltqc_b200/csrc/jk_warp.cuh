@@ -162,7 +162,7 @@ struct WarpPlan {
 };
 
 #ifndef JQC_WARP_REGS
-#define JQC_WARP_REGS 128   // register budget per thread of the multi-lane kernel (occupancy lever)
+#define JQC_WARP_REGS 255   // register budget per thread of the multi-lane kernel (occupancy lever)
 #endif
 template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS * 32)) jk_warp_kernel(const JKArgs a)
