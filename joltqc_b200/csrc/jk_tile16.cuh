@@ -82,8 +82,13 @@ __device__ __forceinline__ void reduce16_flush(double (&x)[pad4(NR * NC)], const
     }
 }
 
+// Blocks of up to 27 integrals fit a 128-register budget without spilling: two CTAs per SM double
+// the warps available to hide the latency of the root-table and density gathers.
+template <int LI, int LJ, int LK, int LL>
+constexpr int tile16_min_blocks() { return QuartetShape<LI, LJ, LK, LL>::N <= 27 ? 2 : 1; }
+
 template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS) jk_tile16_kernel(const JKArgs a)
+__global__ void __launch_bounds__(NTHREADS, tile16_min_blocks<LI, LJ, LK, LL>()) jk_tile16_kernel(const JKArgs a)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
