@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -94,6 +95,9 @@ struct jqc_engine {
     DevBuf<unsigned> d_counters;
     DevBuf<unsigned long long> d_qcounts;
     int rank = 0, world = 1;
+    // task format for blocks of <= 81 integrals: 0 flat quartets (default), 1 4x4 tile records.
+    // Both were measured in round 1 (profiles/README.md); JQC_SMALL_TILES=1 selects the tile kernel.
+    int small_tiles = 0;
     // state of the last build
     int last_n = 0, last_neff = 0, last_hermi = 1, last_j = 0, last_k = 0, launches = 0;
     bool built = false, profiling = false;
@@ -119,6 +123,7 @@ extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine
     CU(cudaSetDevice(device));
     std::unique_ptr<jqc_engine> e(new jqc_engine);
     e->device = device;
+    if (const char* m = getenv("JQC_SMALL_TILES")) e->small_tiles = atoi(m) != 0;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     e->nsm = prop.multiProcessorCount;
@@ -456,7 +461,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             s.queue = e->d_queue.p;
             s.counter = e->d_counters.p + cid;
             s.qcount = e->d_qcounts.p + cid;
-            s.tile_mode = jk_uses_tiles(li, lj, lk, ll) ? 1 : 0;
+            s.tile_mode = (e->small_tiles && jk_uses_tiles(li, lj, lk, ll)) ? 1 : 0;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (e->profiling) {
                 while (e->ev.size() < nev + 2) { cudaEvent_t x; CU(cudaEventCreate(&x)); e->ev.push_back(x); }
@@ -477,7 +482,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             a.omega = omega;
             a.quartets = e->d_queue.p;
             a.ntasks = e->d_counters.p + cid;
-            CU(jk_launch(li, lj, lk, ll, variant, a, e->nsm, st));
+            CU(jk_launch(li, lj, lk, ll, variant | (s.tile_mode ? 4 : 0), a, e->nsm, st));
             if (e->profiling) CU(cudaEventRecord(e1, st));
             e->launches += 2;
             e->chunks.push_back({key, pw});

@@ -39,16 +39,21 @@ struct QuartetShape {
 
 constexpr int JQC_SMALL_N = 81;
 
+// register-resident variant: blocks of <= 27 integrals fit 128 registers (two CTAs per SM)
+#define JQC_MINB(a, b, c, d) (QuartetShape<a, b, c, d>::N <= 27 ? 2 : 1)
 #define JQC_NAME(x) x##_small
 #define JQC_UNROLL _Pragma("unroll")
 #include "jk_1q1t_body.inc"
 #undef JQC_NAME
 #undef JQC_UNROLL
+#undef JQC_MINB
 
+#define JQC_MINB(a, b, c, d) 1
 #define JQC_NAME(x) x##_large
 #define JQC_UNROLL _Pragma("unroll 1")
 #include "jk_1q1t_body.inc"
 #undef JQC_NAME
 #undef JQC_UNROLL
+#undef JQC_MINB
 
 }  // namespace jqc

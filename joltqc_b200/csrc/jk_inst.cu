@@ -43,7 +43,7 @@ static cudaError_t launch_warp(const JKArgs& a, int nsm, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int LK, int LL, bool DO_J, bool DO_K>
+template <int LK, int LL, bool DO_J, bool DO_K, bool TILES>
 static cudaError_t launch_one(const JKArgs& a, int nsm, cudaStream_t st)
 {
     using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
@@ -54,7 +54,8 @@ static cudaError_t launch_one(const JKArgs& a, int nsm, cudaStream_t st)
     constexpr int NT = SMALL ? 256 : 128;
     static_assert(JQC_SMALL_N == 81, "keep jk_uses_tiles() in jk_launch.h in sync");
     void (*kern)(const JKArgs);
-    if constexpr (SMALL) kern = jk_tile16_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
+    if constexpr (SMALL) kern = TILES ? jk_tile16_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>
+                                      : jk_1q1t_kernel_small<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
     else kern = jk_1q1t_kernel_large<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
@@ -70,10 +71,15 @@ static cudaError_t launch_one(const JKArgs& a, int nsm, cudaStream_t st)
 template <int LK, int LL>
 static cudaError_t launch_variant(int variant, const JKArgs& a, int nsm, cudaStream_t st)
 {
+    // bit 2 of the variant selects the tile-record kernel for the small classes
+    constexpr bool SM = QuartetShape<JQC_LI, JQC_LJ, LK, LL>::N <= JQC_SMALL_N;
     switch (variant) {
-        case 3: return launch_one<LK, LL, true, true>(a, nsm, st);
-        case 1: return launch_one<LK, LL, true, false>(a, nsm, st);
-        case 2: return launch_one<LK, LL, false, true>(a, nsm, st);
+        case 3: return launch_one<LK, LL, true, true, false>(a, nsm, st);
+        case 1: return launch_one<LK, LL, true, false, false>(a, nsm, st);
+        case 2: return launch_one<LK, LL, false, true, false>(a, nsm, st);
+        case 7: if constexpr (SM) return launch_one<LK, LL, true, true, true>(a, nsm, st); break;
+        case 5: if constexpr (SM) return launch_one<LK, LL, true, false, true>(a, nsm, st); break;
+        case 6: if constexpr (SM) return launch_one<LK, LL, false, true, true>(a, nsm, st); break;
     }
     return cudaErrorInvalidValue;
 }
