@@ -41,19 +41,23 @@ constexpr int JQC_SMALL_N = 81;
 
 // register-resident variant: blocks of <= 27 integrals fit 128 registers (two CTAs per SM)
 #define JQC_MINB(a, b, c, d) (QuartetShape<a, b, c, d>::N <= 27 ? 2 : 1)
+#define JQC_WARP_COMBINE true
 #define JQC_NAME(x) x##_small
 #define JQC_UNROLL _Pragma("unroll")
 #include "jk_1q1t_body.inc"
 #undef JQC_NAME
 #undef JQC_UNROLL
 #undef JQC_MINB
+#undef JQC_WARP_COMBINE
 
 #define JQC_MINB(a, b, c, d) 1
+#define JQC_WARP_COMBINE false
 #define JQC_NAME(x) x##_large
 #define JQC_UNROLL _Pragma("unroll 1")
 #include "jk_1q1t_body.inc"
 #undef JQC_NAME
 #undef JQC_UNROLL
 #undef JQC_MINB
+#undef JQC_WARP_COMBINE
 
 }  // namespace jqc
