@@ -369,19 +369,30 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
 #pragma unroll 1
             for (int b = 0; b < a.n_dm; b++) {
                 const double* __restrict__ dm = a.dm + b * nao2;
-                // stage the six density blocks of this quartet (coalesced over the group)
+                // stage the six density blocks of this quartet (coalesced over the group); fully
+                // unrolled so that all gathers are in flight before the first shared-memory store
                 if (active) {
-                    for (int e = t; e < NIJ; e += T) { const int j = e / NFI, i = e - j * NFI; s_d[D_JI + e] = __ldg(dm + (size_t)(j0 + j) * nao + i0 + i); }
-                    for (int e = t; e < NKL; e += T) { const int l = e / NFK, k = e - l * NFK; s_d[D_LK + e] = __ldg(dm + (size_t)(l0 + l) * nao + k0 + k); }
+#define JQC_STAGE(OFF, NR, NC, R0, C0)                                                             \
+    _Pragma("unroll") for (int m = 0; m < ((NR) * (NC) + T - 1) / T; m++) {                        \
+        const int e = t + m * T;                                                                   \
+        if (e < (NR) * (NC)) { const int r = e / (NC), c = e - r * (NC);                           \
+            s_d[(OFF) + e] = __ldg(dm + (size_t)((R0) + r) * nao + (C0) + c); }                    \
+    }
+                    JQC_STAGE(D_JI, NFJ, NFI, j0, i0)
+                    JQC_STAGE(D_LK, NFL, NFK, l0, k0)
                     if constexpr (DO_K) {
-                        for (int e = t; e < NFJ * NFL; e += T) { const int j = e / NFL, l = e - j * NFL; s_d[D_JL + e] = __ldg(dm + (size_t)(j0 + j) * nao + l0 + l); }
-                        for (int e = t; e < NFJ * NFK; e += T) { const int j = e / NFK, k = e - j * NFK; s_d[D_JK + e] = __ldg(dm + (size_t)(j0 + j) * nao + k0 + k); }
-                        for (int e = t; e < NFI * NFL; e += T) { const int i = e / NFL, l = e - i * NFL; s_d[D_IL + e] = __ldg(dm + (size_t)(i0 + i) * nao + l0 + l); }
-                        for (int e = t; e < NFI * NFK; e += T) { const int i = e / NFK, k = e - i * NFK; s_d[D_IK + e] = __ldg(dm + (size_t)(i0 + i) * nao + k0 + k); }
+                        JQC_STAGE(D_JL, NFJ, NFL, j0, l0)
+                        JQC_STAGE(D_JK, NFJ, NFK, j0, k0)
+                        JQC_STAGE(D_IL, NFI, NFL, i0, l0)
+                        JQC_STAGE(D_IK, NFI, NFK, i0, k0)
                     }
+#undef JQC_STAGE
                 }
                 __syncwarp();
                 if (active) {
+                    double dlk[NKLP];
+#pragma unroll
+                    for (int s = 0; s < NKLP; s++) dlk[s] = pv[s] ? s_d[D_LK + pl[s] * NFK + pk[s]] : 0.0;
 #pragma unroll
                     for (int s = 0; s < NKLP; s++) {
                         if (!pv[s]) continue;
@@ -400,14 +411,27 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
                             }
                         }
                         if constexpr (DO_K) {
+                            // density columns this pair needs, fetched once (the staging stores below
+                            // would otherwise force the compiler to reload them for every element)
+                            double djl[NJC], djk[NJC], dil[NFI], dik[NFI];
+#pragma unroll
+                            for (int jj = 0; jj < NJC; jj++) {
+                                djl[jj] = s_d[D_JL + (jc0 + jj) * NFL + lc];
+                                djk[jj] = s_d[D_JK + (jc0 + jj) * NFK + kc];
+                            }
+#pragma unroll
+                            for (int i = 0; i < NFI; i++) {
+                                dil[i] = s_d[D_IL + i * NFL + lc];
+                                dik[i] = s_d[D_IK + i * NFK + kc];
+                            }
                             // K_ik partial: a[i] = sum_j (ij|kl) D[j,l];  K_il partial: b[i] = sum_j (ij|kl) D[j,k]
 #pragma unroll
                             for (int i = 0; i < NFI; i++) {
                                 double va = 0.0, vb = 0.0;
 #pragma unroll
                                 for (int jj = 0; jj < NJC; jj++) {
-                                    va = fma(acc[s][jj * NFI + i], s_d[D_JL + (jc0 + jj) * NFL + lc], va);
-                                    vb = fma(acc[s][jj * NFI + i], s_d[D_JK + (jc0 + jj) * NFK + kc], vb);
+                                    va = fma(acc[s][jj * NFI + i], djl[jj], va);
+                                    vb = fma(acc[s][jj * NFI + i], djk[jj], vb);
                                 }
                                 if (pass == 0 || per_pass_flush) { s_st[ST_IK + p * NFI + i] = va; s_st[ST_IL + p * NFI + i] = vb; }
                                 else { s_st[ST_IK + p * NFI + i] += va; s_st[ST_IL + p * NFI + i] += vb; }
@@ -418,8 +442,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
                                 double vc = 0.0, vd = 0.0;
 #pragma unroll
                                 for (int i = 0; i < NFI; i++) {
-                                    vc = fma(acc[s][jj * NFI + i], s_d[D_IL + i * NFL + lc], vc);
-                                    vd = fma(acc[s][jj * NFI + i], s_d[D_IK + i * NFK + kc], vd);
+                                    vc = fma(acc[s][jj * NFI + i], dil[i], vc);
+                                    vd = fma(acc[s][jj * NFI + i], dik[i], vd);
                                 }
                                 s_st[ST_JK + p * NFJ + jc0 + jj] = vc;
                                 s_st[ST_JL + p * NFJ + jc0 + jj] = vd;
@@ -434,8 +458,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
                             for (int i = 0; i < NFI; i++) {
                                 double v = 0.0;
 #pragma unroll
-                                for (int s = 0; s < NKLP; s++)
-                                    if (pv[s]) v = fma(acc[s][jj * NFI + i], s_d[D_LK + pl[s] * NFK + pk[s]], v);
+                                for (int s = 0; s < NKLP; s++) v = fma(acc[s][jj * NFI + i], dlk[s], v);
                                 s_st[ST_IJ + t * NIJ + (jc0 + jj) * NFI + i] = v;
                             }
                     }
