@@ -50,55 +50,43 @@ __device__ __forceinline__ void rys_root_one(double x, int i, double& root, doub
     weight = fma(u, w1, a.y) - w2;
 }
 
-// TRR + in-place HRR for K independent (root, direction) arrays at once.  The recurrences of one
-// array are long dependent FP64 chains; running K of them in lock step gives the scheduler K
-// independent chains per lane (the kernel has only ~2 warps per scheduler to hide latency with).
-template <int LI, int LJ, int LK, int LL, int K>
-__device__ __forceinline__ void fill_g_multi(double* const (&gd)[K], const double (&seed)[K], const double (&c0)[K],
-                                             const double (&cp)[K], const double (&b10)[K], const double (&b01)[K],
-                                             const double (&b00)[K], const double (&ab)[K], const double (&cd)[K])
+// TRR + in-place HRR for one cartesian direction into gd[GSIZE] (shared memory).
+template <int LI, int LJ, int LK, int LL>
+__device__ __forceinline__ void fill_g_dir(double* __restrict__ gd, const double seed, const double c0, const double cp,
+                                           const double b10, const double b01, const double b00, const double ab,
+                                           const double cd)
 {
     // shared-memory strides: DK padded to an odd number of doubles so that the (k,l) slots that
     // different lanes read in the product phase fall into different banks; DL keeps the exact
     // (LK+1)*DK aliasing the in-place HRR relies on.
     using S = QuartetShape<LI, LJ, LK, LL>;
     constexpr int DJ = S::DJ, DK = S::DK | 1, DL = DK * (LK + 1), LIJ = S::LIJ, LKL = S::LKL;
-#pragma unroll
-    for (int q = 0; q < K; q++) gd[q][0] = seed[q];
+    gd[0] = seed;
     if constexpr (LIJ > 0) {
-        double s0[K], s1[K];
-#pragma unroll
-        for (int q = 0; q < K; q++) { s0[q] = seed[q]; s1[q] = c0[q] * seed[q]; gd[q][1] = s1[q]; }
+        double s0 = seed, s1 = c0 * seed;
+        gd[1] = s1;
 #pragma unroll
         for (int i = 1; i < LIJ; i++) {
-#pragma unroll
-            for (int q = 0; q < K; q++) {
-                const double s2 = fma(c0[q], s1[q], (i * b10[q]) * s0[q]);
-                gd[q][i + 1] = s2;
-                s0[q] = s1[q]; s1[q] = s2;
-            }
+            const double s2 = fma(c0, s1, (i * b10) * s0);
+            gd[i + 1] = s2;
+            s0 = s1; s1 = s2;
         }
     }
     if constexpr (LKL > 0) {
 #pragma unroll
         for (int i = 0; i <= LIJ; i++) {
-#pragma unroll
-            for (int q = 0; q < K; q++) {
-                double v = cp[q] * gd[q][i];
-                if (i > 0) v = fma(i * b00[q], gd[q][i - 1], v);
-                gd[q][i + DK] = v;
-            }
+            double v = cp * gd[i];
+            if (i > 0) v = fma(i * b00, gd[i - 1], v);
+            gd[i + DK] = v;
         }
 #pragma unroll
         for (int k = 1; k < LKL; k++) {
+            const double kb01 = k * b01;
 #pragma unroll
             for (int i = 0; i <= LIJ; i++) {
-#pragma unroll
-                for (int q = 0; q < K; q++) {
-                    double v = fma(cp[q], gd[q][i + k * DK], (k * b01[q]) * gd[q][i + (k - 1) * DK]);
-                    if (i > 0) v = fma(i * b00[q], gd[q][i - 1 + k * DK], v);
-                    gd[q][i + (k + 1) * DK] = v;
-                }
+                double v = fma(cp, gd[i + k * DK], kb01 * gd[i + (k - 1) * DK]);
+                if (i > 0) v = fma(i * b00, gd[i - 1 + k * DK], v);
+                gd[i + (k + 1) * DK] = v;
             }
         }
     }
@@ -110,8 +98,7 @@ __device__ __forceinline__ void fill_g_multi(double* const (&gd)[K], const doubl
 #pragma unroll
                 for (int i = LIJ - j - 1; i >= 0; i--) {
                     const int src = i + j * DJ + k * DK;
-#pragma unroll
-                    for (int q = 0; q < K; q++) gd[q][src + DJ] = fma(-ab[q], gd[q][src], gd[q][src + 1]);
+                    gd[src + DJ] = fma(-ab, gd[src], gd[src + 1]);
                 }
     }
     if constexpr (LL > 0) {
@@ -122,8 +109,7 @@ __device__ __forceinline__ void fill_g_multi(double* const (&gd)[K], const doubl
 #pragma unroll
                 for (int k = LKL - l - 1; k >= 0; k--) {
                     const int src = ij + k * DK + l * DL;
-#pragma unroll
-                    for (int q = 0; q < K; q++) gd[q][src + DL] = fma(-cd[q], gd[q][src], gd[q][src + DK]);
+                    gd[src + DL] = fma(-cd, gd[src], gd[src + DK]);
                 }
     }
 }
@@ -311,31 +297,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
                         }
                     }
                     __syncwarp();
-                    // recurrences: item = (root, direction); a lane runs its items interleaved
+                    // recurrences: item = (root, direction)
                     if (active) {
-                        constexpr int NIT = (3 * NROOTS + T - 1) / T;
-                        double* gp[NIT];
-                        double seed[NIT], c0[NIT], cp[NIT], b10[NIT], b01[NIT], b00[NIT], ab[NIT], cd[NIT];
-#pragma unroll
-                        for (int q = 0; q < NIT; q++) {
-                            int item = t + q * T;
-                            if (item >= 3 * NROOTS) item = t;      // duplicate of the lane's first item (same stores)
+#pragma unroll 1
+                        for (int item = t; item < 3 * NROOTS; item += T) {
                             const int r = item / 3, d = item - 3 * r;
                             const double rt = s_rw[2 * r], wt = s_rw[2 * r + 1];
                             const double rt_aa = rt * inv_aijkl;
                             const double rt_aij = rt_aa * akl, rt_akl = rt_aa * aij;
-                            b10[q] = 0.5 * inv_aij * (1.0 - rt_aij);
-                            b01[q] = 0.5 * inv_akl * (1.0 - rt_akl);
-                            b00[q] = 0.5 * rt_aa;
-                            ab[q] = d == 0 ? rjri[0] : (d == 1 ? rjri[1] : rjri[2]);
-                            cd[q] = d == 0 ? rlrk[0] : (d == 1 ? rlrk[1] : rlrk[2]);
+                            const double b10 = 0.5 * inv_aij * (1.0 - rt_aij);
+                            const double b01 = 0.5 * inv_akl * (1.0 - rt_akl);
+                            const double b00 = 0.5 * rt_aa;
+                            const double ab = d == 0 ? rjri[0] : (d == 1 ? rjri[1] : rjri[2]);
+                            const double cd = d == 0 ? rlrk[0] : (d == 1 ? rlrk[1] : rlrk[2]);
                             const double pq = d == 0 ? Rpq[0] : (d == 1 ? Rpq[1] : Rpq[2]);
-                            seed[q] = d == 0 ? ckcl : (d == 1 ? gy0 : wt);
-                            c0[q] = fma(ab[q], aj_aij, -rt_aij * pq);
-                            cp[q] = fma(cd[q], al_akl, rt_akl * pq);
-                            gp[q] = s_g + (size_t)item * GS;
+                            const double seed = d == 0 ? ckcl : (d == 1 ? gy0 : wt);
+                            const double c0 = fma(ab, aj_aij, -rt_aij * pq);
+                            const double cp = fma(cd, al_akl, rt_akl * pq);
+                            fill_g_dir<LI, LJ, LK, LL>(s_g + (size_t)item * GS, seed, c0, cp, b10, b01, b00, ab, cd);
                         }
-                        if (t < 3 * NROOTS) fill_g_multi<LI, LJ, LK, LL, NIT>(gp, seed, c0, cp, b10, b01, b00, ab, cd);
                     }
                     __syncwarp();
                     // product: this lane's pairs x (i, j in pass) over all roots
