@@ -353,10 +353,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
                 // unrolled so that all gathers are in flight before the first shared-memory store
                 if (active) {
 #define JQC_STAGE(OFF, NR, NC, R0, C0)                                                             \
-    _Pragma("unroll") for (int m = 0; m < ((NR) * (NC) + T - 1) / T; m++) {                        \
-        const int e = t + m * T;                                                                   \
-        if (e < (NR) * (NC)) { const int r = e / (NC), c = e - r * (NC);                           \
-            s_d[(OFF) + e] = __ldg(dm + (size_t)((R0) + r) * nao + (C0) + c); }                    \
+    {                                                                                              \
+        constexpr int CW = (NC) < T ? (NC) : T, RT = T / CW;                                       \
+        const int rr = t / CW, cc = t - rr * CW;                                                   \
+        if (rr < RT) {                                                                             \
+            _Pragma("unroll") for (int mr = 0; mr < ((NR) + RT - 1) / RT; mr++) {                  \
+                const int r = rr + mr * RT;                                                        \
+                if (r < (NR)) {                                                                    \
+                    const double* __restrict__ src = dm + (size_t)((R0) + r) * nao + (C0) + cc;   \
+                    double* __restrict__ dst = s_d + (OFF) + r * (NC) + cc;                        \
+                    _Pragma("unroll") for (int mc = 0; mc < ((NC) + CW - 1) / CW; mc++)            \
+                        if (cc + mc * CW < (NC)) dst[mc * CW] = __ldg(src + mc * CW);              \
+                }                                                                                  \
+            }                                                                                      \
+        }                                                                                          \
     }
                     JQC_STAGE(D_JI, NFJ, NFI, j0, i0)
                     JQC_STAGE(D_LK, NFL, NFK, l0, k0)
@@ -449,15 +459,29 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
                     if (active) {
                         const bool partial_j = per_pass_flush;   // then only this pass' j range is valid
                         const int jlo = partial_j ? jc0 : 0, jhi = partial_j ? jc0 + NJC : NFJ;
+// lanes of the group tile a block as (RT rows) x (CW columns); rows/columns advance by compile-time
+// steps so that every address is one base plus immediates (no per-element division)
+#define JQC_FLUSH(NR, NC, RLO, RHI, EXPR, DEST)                                                    \
+    {                                                                                              \
+        constexpr int CW = (NC) < T ? (NC) : T, RT = T / CW;                                       \
+        const int rr = t / CW, cc = t - rr * CW;                                                   \
+        if (rr < RT) {                                                                             \
+            _Pragma("unroll") for (int mr = 0; mr < ((NR) + RT - 1) / RT; mr++) {                  \
+                const int r = rr + mr * RT;                                                        \
+                if (r >= (RLO) && r < (RHI)) {                                                     \
+                    _Pragma("unroll") for (int mc = 0; mc < ((NC) + CW - 1) / CW; mc++) {          \
+                        const int c = cc + mc * CW;                                                \
+                        if (c < (NC)) { double v = 0.0; EXPR; atomicAdd(DEST, v); }                \
+                    }                                                                              \
+                }                                                                                  \
+            }                                                                                      \
+        }                                                                                          \
+    }
                         if constexpr (DO_J) {
                             double* __restrict__ vj = a.vj + b * nao2;
-                            for (int e = t + jlo * NFI; e < jhi * NFI; e += T) {
-                                double v = 0.0;
-#pragma unroll
-                                for (int u = 0; u < T; u++) v += s_st[ST_IJ + u * NIJ + e];
-                                const int j = e / NFI, i = e - j * NFI;
-                                atomicAdd(vj + (size_t)(j0 + j) * nao + i0 + i, v);
-                            }
+                            JQC_FLUSH(NFJ, NFI, jlo, jhi,
+                                      _Pragma("unroll") for (int u = 0; u < T; u++) v += s_st[ST_IJ + u * NIJ + r * NFI + c],
+                                      vj + (size_t)(j0 + r) * nao + i0 + c)
                             if (NPASS > 1 && !per_pass_flush) {
 #pragma unroll
                                 for (int s = 0; s < NKLP; s++)
@@ -466,36 +490,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
                         }
                         if constexpr (DO_K) {
                             double* __restrict__ vk = a.vk + b * nao2;
-                            // with n_dm > 1 and several passes the i-vectors were overwritten per pass: flush each pass
-                            for (int e = t; e < NFI * NFK; e += T) {
-                                const int i = e / NFK, k = e - i * NFK;
-                                double v = 0.0;
-#pragma unroll
-                                for (int l = 0; l < NFL; l++) v += s_st[ST_IK + (l * NFK + k) * NFI + i];
-                                atomicAdd(vk + (size_t)(i0 + i) * nao + k0 + k, v);
-                            }
-                            for (int e = t; e < NFI * NFL; e += T) {
-                                const int i = e / NFL, l = e - i * NFL;
-                                double v = 0.0;
-#pragma unroll
-                                for (int k = 0; k < NFK; k++) v += s_st[ST_IL + (l * NFK + k) * NFI + i];
-                                atomicAdd(vk + (size_t)(i0 + i) * nao + l0 + l, v);
-                            }
-                            for (int e = t + jlo * NFK; e < jhi * NFK; e += T) {
-                                const int j = e / NFK, k = e - j * NFK;
-                                double v = 0.0;
-#pragma unroll
-                                for (int l = 0; l < NFL; l++) v += s_st[ST_JK + (l * NFK + k) * NFJ + j];
-                                atomicAdd(vk + (size_t)(j0 + j) * nao + k0 + k, v);
-                            }
-                            for (int e = t + jlo * NFL; e < jhi * NFL; e += T) {
-                                const int j = e / NFL, l = e - j * NFL;
-                                double v = 0.0;
-#pragma unroll
-                                for (int k = 0; k < NFK; k++) v += s_st[ST_JL + (l * NFK + k) * NFJ + j];
-                                atomicAdd(vk + (size_t)(j0 + j) * nao + l0 + l, v);
-                            }
+                            JQC_FLUSH(NFI, NFK, 0, NFI,
+                                      _Pragma("unroll") for (int l = 0; l < NFL; l++) v += s_st[ST_IK + (l * NFK + c) * NFI + r],
+                                      vk + (size_t)(i0 + r) * nao + k0 + c)
+                            JQC_FLUSH(NFI, NFL, 0, NFI,
+                                      _Pragma("unroll") for (int k = 0; k < NFK; k++) v += s_st[ST_IL + (c * NFK + k) * NFI + r],
+                                      vk + (size_t)(i0 + r) * nao + l0 + c)
+                            JQC_FLUSH(NFJ, NFK, jlo, jhi,
+                                      _Pragma("unroll") for (int l = 0; l < NFL; l++) v += s_st[ST_JK + (l * NFK + c) * NFJ + r],
+                                      vk + (size_t)(j0 + r) * nao + k0 + c)
+                            JQC_FLUSH(NFJ, NFL, jlo, jhi,
+                                      _Pragma("unroll") for (int k = 0; k < NFK; k++) v += s_st[ST_JL + (c * NFK + k) * NFJ + r],
+                                      vk + (size_t)(j0 + r) * nao + l0 + c)
                         }
+#undef JQC_FLUSH
                     }
                     __syncwarp();
                 }
