@@ -114,6 +114,17 @@ __device__ __forceinline__ void fill_g_dir(double* __restrict__ gd, const double
     }
 }
 
+// Lane map for cooperative passes over an NR x NC block by T lanes: a 2-D (rows x columns) tiling
+// needs no per-element division but may leave lanes idle; it is used when it loses < 15 % of the
+// slots relative to the flattened (e = t + m T) map.
+__host__ __device__ constexpr bool use_2d_map(int NR, int NC, int T)
+{
+    const int CW = NC < T ? NC : T, RT = T / CW;
+    const int it2d = ((NR + RT - 1) / RT) * ((NC + CW - 1) / CW);
+    const int itflat = (NR * NC + T - 1) / T;
+    return it2d * 100 <= itflat * 115;
+}
+
 // ---- per-class lane layout ---------------------------------------------------------------
 constexpr int WARP_ACC_MAX = 60;   // doubles of (i,j)-block accumulators per lane
 
@@ -353,7 +364,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
                 // unrolled so that all gathers are in flight before the first shared-memory store
                 if (active) {
 #define JQC_STAGE(OFF, NR, NC, R0, C0)                                                             \
-    {                                                                                              \
+    if constexpr (!use_2d_map(NR, NC, T)) {                                                        \
+        _Pragma("unroll") for (int m = 0; m < ((NR) * (NC) + T - 1) / T; m++) {                    \
+            const int e = t + m * T;                                                               \
+            if (e < (NR) * (NC)) { const int r = e / (NC), c = e - r * (NC);                       \
+                s_d[(OFF) + e] = __ldg(dm + (size_t)((R0) + r) * nao + (C0) + c); }                \
+        }                                                                                          \
+    } else {                                                                                       \
         constexpr int CW = (NC) < T ? (NC) : T, RT = T / CW;                                       \
         const int rr = t / CW, cc = t - rr * CW;                                                   \
         if (rr < RT) {                                                                             \
@@ -462,7 +479,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
 // lanes of the group tile a block as (RT rows) x (CW columns); rows/columns advance by compile-time
 // steps so that every address is one base plus immediates (no per-element division)
 #define JQC_FLUSH(NR, NC, RLO, RHI, EXPR, DEST)                                                    \
-    {                                                                                              \
+    if constexpr (!use_2d_map(NR, NC, T)) {                                                        \
+        _Pragma("unroll") for (int m = 0; m < ((NR) * (NC) + T - 1) / T; m++) {                    \
+            const int e = t + m * T;                                                               \
+            const int r = e / (NC), c = e - r * (NC);                                              \
+            if (e < (NR) * (NC) && r >= (RLO) && r < (RHI)) { double v = 0.0; EXPR; atomicAdd(DEST, v); } \
+        }                                                                                          \
+    } else {                                                                                       \
         constexpr int CW = (NC) < T ? (NC) : T, RT = T / CW;                                       \
         const int rr = t / CW, cc = t - rr * CW;                                                   \
         if (rr < RT) {                                                                             \
