@@ -18,6 +18,16 @@
 
 namespace jqc {
 
+// 8-byte asynchronous global->shared copy (LDGSTS): the density blocks of a quartet are fetched
+// while the lanes are busy with the recurrences and products, without holding registers.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // One Rys root/weight (index i of NROOTS) at argument x.
 template <int NROOTS>
 __device__ __forceinline__ void rys_root_one(double x, int i, double& root, double& weight)
@@ -172,6 +182,39 @@ struct WarpPlan {
     static constexpr int PER_GROUP = END | 1;            // odd stride between quartet groups
 };
 
+// cooperative staging of the six density blocks of a quartet into s_d (JQC_COPY = load op)
+#define JQC_STAGE(OFF, NR, NC, R0, C0)                                                             \
+    if constexpr (!use_2d_map(NR, NC, T)) {                                                        \
+        _Pragma("unroll") for (int m = 0; m < ((NR) * (NC) + T - 1) / T; m++) {                    \
+            const int e = t + m * T;                                                               \
+            if (e < (NR) * (NC)) { const int r = e / (NC), c = e - r * (NC);                       \
+                JQC_COPY(s_d + (OFF) + e, dm + (size_t)((R0) + r) * nao + (C0) + c); }                \
+        }                                                                                          \
+    } else {                                                                                       \
+        constexpr int CW = (NC) < T ? (NC) : T, RT = T / CW;                                       \
+        const int rr = t / CW, cc = t - rr * CW;                                                   \
+        if (rr < RT) {                                                                             \
+            _Pragma("unroll") for (int mr = 0; mr < ((NR) + RT - 1) / RT; mr++) {                  \
+                const int r = rr + mr * RT;                                                        \
+                if (r < (NR)) {                                                                    \
+                    const double* __restrict__ src = dm + (size_t)((R0) + r) * nao + (C0) + cc;   \
+                    double* __restrict__ dst = s_d + (OFF) + r * (NC) + cc;                        \
+                    _Pragma("unroll") for (int mc = 0; mc < ((NC) + CW - 1) / CW; mc++)            \
+                        if (cc + mc * CW < (NC)) JQC_COPY(dst + mc * CW, src + mc * CW);              \
+                }                                                                                  \
+            }                                                                                      \
+        }                                                                                          \
+    }
+#define JQC_STAGE_ALL                                  \
+    JQC_STAGE(D_JI, NFJ, NFI, j0, i0)                  \
+    JQC_STAGE(D_LK, NFL, NFK, l0, k0)                  \
+    if constexpr (DO_K) {                              \
+        JQC_STAGE(D_JL, NFJ, NFL, j0, l0)              \
+        JQC_STAGE(D_JK, NFJ, NFK, j0, k0)              \
+        JQC_STAGE(D_IL, NFI, NFL, i0, l0)              \
+        JQC_STAGE(D_IK, NFI, NFK, i0, k0)              \
+    }
+
 #ifndef JQC_WARP_REGS
 #define JQC_WARP_REGS 255   // register budget per thread of the multi-lane kernel (occupancy lever)
 #endif
@@ -244,6 +287,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
         const double rr_ij = rjri[0] * rjri[0] + rjri[1] * rjri[1] + rjri[2] * rjri[2];
         const double rr_kl = rlrk[0] * rlrk[0] + rlrk[1] * rlrk[1] + rlrk[2] * rlrk[2];
         const int i0 = (int)ri.w, j0 = (int)rj.w, k0 = (int)rk.w, l0 = (int)rl.w;
+        {   // prefetch the density blocks of matrix 0 (consumed after the products)
+            const double* __restrict__ dm = a.dm;
+            if (active) {
+#define JQC_COPY(dst, src) cp_async8(dst, src)
+                JQC_STAGE_ALL
+#undef JQC_COPY
+            }
+            cp_async_commit();
+        }
 
         // With several bra passes and one density matrix the partial sums are carried across the
         // passes (jkl in registers, i-vectors in the staging area) and flushed once; with several
@@ -360,40 +412,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
 #pragma unroll 1
             for (int b = 0; b < a.n_dm; b++) {
                 const double* __restrict__ dm = a.dm + b * nao2;
-                // stage the six density blocks of this quartet (coalesced over the group); fully
-                // unrolled so that all gathers are in flight before the first shared-memory store
-                if (active) {
-#define JQC_STAGE(OFF, NR, NC, R0, C0)                                                             \
-    if constexpr (!use_2d_map(NR, NC, T)) {                                                        \
-        _Pragma("unroll") for (int m = 0; m < ((NR) * (NC) + T - 1) / T; m++) {                    \
-            const int e = t + m * T;                                                               \
-            if (e < (NR) * (NC)) { const int r = e / (NC), c = e - r * (NC);                       \
-                s_d[(OFF) + e] = __ldg(dm + (size_t)((R0) + r) * nao + (C0) + c); }                \
-        }                                                                                          \
-    } else {                                                                                       \
-        constexpr int CW = (NC) < T ? (NC) : T, RT = T / CW;                                       \
-        const int rr = t / CW, cc = t - rr * CW;                                                   \
-        if (rr < RT) {                                                                             \
-            _Pragma("unroll") for (int mr = 0; mr < ((NR) + RT - 1) / RT; mr++) {                  \
-                const int r = rr + mr * RT;                                                        \
-                if (r < (NR)) {                                                                    \
-                    const double* __restrict__ src = dm + (size_t)((R0) + r) * nao + (C0) + cc;   \
-                    double* __restrict__ dst = s_d + (OFF) + r * (NC) + cc;                        \
-                    _Pragma("unroll") for (int mc = 0; mc < ((NC) + CW - 1) / CW; mc++)            \
-                        if (cc + mc * CW < (NC)) dst[mc * CW] = __ldg(src + mc * CW);              \
-                }                                                                                  \
-            }                                                                                      \
-        }                                                                                          \
-    }
-                    JQC_STAGE(D_JI, NFJ, NFI, j0, i0)
-                    JQC_STAGE(D_LK, NFL, NFK, l0, k0)
-                    if constexpr (DO_K) {
-                        JQC_STAGE(D_JL, NFJ, NFL, j0, l0)
-                        JQC_STAGE(D_JK, NFJ, NFK, j0, k0)
-                        JQC_STAGE(D_IL, NFI, NFL, i0, l0)
-                        JQC_STAGE(D_IK, NFI, NFK, i0, k0)
-                    }
-#undef JQC_STAGE
+                // density blocks: the first matrix was prefetched with cp.async at the top of the batch
+                // (first pass); later matrices / passes are staged here synchronously
+                if (b == 0 && pass == 0) {
+                    cp_async_wait_all();
+                } else if (active && a.n_dm > 1) {   // one matrix: s_d still holds it from pass 0
+#define JQC_COPY(dst, src) *(dst) = __ldg(src)
+                    JQC_STAGE_ALL
+#undef JQC_COPY
                 }
                 __syncwarp();
                 if (active) {
