@@ -179,7 +179,16 @@ struct WarpPlan {
     static constexpr int OFF_D = OFF_G + (ALIAS ? (G_ALL > STAGE ? G_ALL : STAGE) : G_ALL);
     static constexpr int OFF_STAGE = ALIAS ? OFF_G : OFF_D + NDBLK;
     static constexpr int END = ALIAS ? OFF_D + NDBLK : OFF_STAGE + STAGE;
-    static constexpr int PER_GROUP = END | 1;            // odd stride between quartet groups
+    // stride between quartet groups: congruent to T*IS mod 16 doubles, so that lane (group g, t)
+    // of a warp sees offset (g*T + t)*IS mod 16 — the 16 lanes of a half-warp then fall into 16
+    // different 8-byte bank pairs whenever they address "own slot + common offset"
+    static constexpr int per_group()
+    {
+        int pg = END;
+        while ((pg - T * IS) % 16 != 0) pg++;
+        return pg;
+    }
+    static constexpr int PER_GROUP = per_group();
 };
 
 // cooperative staging of the six density blocks of a quartet into s_d (JQC_COPY = load op)
