@@ -136,11 +136,10 @@ __host__ __device__ constexpr bool use_2d_map(int NR, int NC, int T)
 }
 
 // ---- per-class lane layout ---------------------------------------------------------------
-// Two register budgets: 60 accumulator doubles per lane with 255 registers (8 warps/SM), or 40
-// with 168 registers (12 warps/SM).  The lighter plan is used when it keeps >= 80 % of the lane
-// slots busy (the kernel is latency bound, more resident warps pay off).
-template <int LI, int LJ, int LK, int LL, int WARP_ACC_MAX>
-struct WarpPlanT {
+constexpr int WARP_ACC_MAX = 60;   // doubles of (i,j)-block accumulators per lane
+
+template <int LI, int LJ, int LK, int LL>
+struct WarpPlan {
     using S = QuartetShape<LI, LJ, LK, LL>;
     static constexpr int NIJ = S::NFI * S::NFJ, NKL = S::NFK * S::NFL;
     // bra passes: split the j components so that one pass keeps <= WARP_ACC_MAX accumulators per pair
@@ -164,12 +163,6 @@ struct WarpPlanT {
             if (eff > best_eff) { best_eff = eff; best = t; }
         }
         return best;
-    }
-    static constexpr int efficiency()   // in 1/1024
-    {
-        const int t = lanes();
-        const int nklp = (NKL + t - 1) / t;
-        return ((32 / t) * t * 1024 / 32) * NKL / (t * nklp);
     }
     static constexpr int T = lanes();
     static constexpr int QPW = 32 / T;
@@ -196,17 +189,6 @@ struct WarpPlanT {
         return pg;
     }
     static constexpr int PER_GROUP = per_group();
-};
-
-template <int LI, int LJ, int LK, int LL>
-constexpr bool warp_light_plan()
-{
-    using L = WarpPlanT<LI, LJ, LK, LL, 40>;
-    return L::NPASS == 1 && L::efficiency() >= 820;
-}
-template <int LI, int LJ, int LK, int LL>
-struct WarpPlan : WarpPlanT<LI, LJ, LK, LL, (warp_light_plan<LI, LJ, LK, LL>() ? 40 : 60)> {
-    static constexpr int REGS = warp_light_plan<LI, LJ, LK, LL>() ? 168 : 255;
 };
 
 // cooperative staging of the six density blocks of a quartet into s_d (JQC_COPY = load op)
@@ -242,9 +224,11 @@ struct WarpPlan : WarpPlanT<LI, LJ, LK, LL, (warp_light_plan<LI, LJ, LK, LL>() ?
         JQC_STAGE(D_IK, NFI, NFK, i0, k0)              \
     }
 
+#ifndef JQC_WARP_REGS
+#define JQC_WARP_REGS 255   // register budget per thread of the multi-lane kernel (occupancy lever)
+#endif
 template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 65536 / (WarpPlan<LI, LJ, LK, LL>::REGS * NWARPS * 32))
-jk_warp_kernel(const JKArgs a)
+__global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS * 32)) jk_warp_kernel(const JKArgs a)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     using P = WarpPlan<LI, LJ, LK, LL>;
