@@ -40,6 +40,11 @@ def generate_jk_kernel(basis_layout: BasisLayout, cutoff_fp64=1e-13, cutoff_fp32
         t0 = time.perf_counter()
         vj, vk = engine.get_jk(dm, hermi=hermi, with_j=with_j, with_k=with_k, omega=omega,
                                cutoff_fp64=cutoff_fp64, cutoff_fp32=cutoff_fp32)
+        if type(dm).__module__.split(".")[0] == "cupy":
+            # GPU4PySCF hands in (and expects back) CuPy arrays: zero-copy views of the results
+            import cupy as cp
+            vj = cp.from_dlpack(vj) if with_j else 0
+            vk = cp.from_dlpack(vk) if with_k else 0
         if getattr(mol, "verbose", 0) >= 5:
             import torch
             torch.cuda.synchronize()
