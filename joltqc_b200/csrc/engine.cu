@@ -70,8 +70,6 @@ struct QData {                    // per-omega Schwarz data
     DevBuf<float> tiles_q;
     DevBuf<int> list_off;         // npairs + 1
     std::vector<int> h_list_off;
-    DevBuf<int> ktiles;           // the same lists in k-major (tile id ascending) order: ket side
-    DevBuf<float> ktiles_q;
 };
 
 struct ChunkRec { int key; long long pw; };   // class key and primitive weight of a launch
@@ -282,8 +280,8 @@ static int get_qdata(jqc_engine* e, double omega, QData** out)
     CU(cudaMemcpy(h_tq.data(), tq.p, h_tq.size() * sizeof(float), cudaMemcpyDeviceToHost));
     // per group pair (gi >= gj): tiles sorted by q descending; tiles that can never pass any
     // realistic cutoff (q = -100 pads) are dropped
-    std::vector<int> tiles, ktiles;
-    std::vector<float> tiles_q, ktiles_q;
+    std::vector<int> tiles;
+    std::vector<float> tiles_q;
     qd->h_list_off.assign(1, 0);
     for (int gi = 0; gi < e->ngroups; gi++)
         for (int gj = 0; gj <= gi; gj++) {
@@ -296,14 +294,10 @@ static int get_qdata(jqc_engine* e, double omega, QData** out)
                 }
             std::sort(v.begin(), v.end());
             for (auto& pr : v) { tiles.push_back(pr.second); tiles_q.push_back(-pr.first); }
-            std::sort(v.begin(), v.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.second < b.second; });
-            for (auto& pr : v) { ktiles.push_back(pr.second); ktiles_q.push_back(-pr.first); }
             qd->h_list_off.push_back((int)tiles.size());
         }
     CU(qd->tiles.upload(tiles));
     CU(qd->tiles_q.upload(tiles_q));
-    CU(qd->ktiles.upload(ktiles));
-    CU(qd->ktiles_q.upload(ktiles_q));
     CU(qd->list_off.upload(qd->h_list_off));
     *out = qd.get();
     e->qcache[omega] = std::move(qd);
@@ -430,9 +424,8 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
     for (int gl = gk; gl >= 0; gl--) {
         const int pij = jqc_engine::pair_id(gi, gj), pkl = jqc_engine::pair_id(gk, gl);
         const int n_ij_all = nact[pij];
-        if (n_ij_all == 0 || nact[pkl] == 0) continue;
-        // the ket side sweeps the static k-major list; the pair cutoff is tested in the generator
-        const int n_kl = qd->h_list_off[pkl + 1] - qd->h_list_off[pkl];
+        const int n_kl = nact[pkl];
+        if (n_ij_all == 0 || n_kl == 0) continue;
         // this rank owns list entries rank, rank + world, ... of the ij list
         const int n_ij = (n_ij_all - e->rank + e->world - 1) / e->world;
         if (n_ij <= 0) continue;
@@ -452,9 +445,8 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             s.logd = e->d_logd.p;
             s.log_max_ordered = e->d_logmax.p;
             s.tiles_ij = qd->tiles.p + qd->h_list_off[pij];
-            s.tiles_kl = qd->ktiles.p + qd->h_list_off[pkl];
-            s.tileq_kl = qd->ktiles_q.p + qd->h_list_off[pkl];
-            s.kl_static = 1;
+            s.tiles_kl = qd->tiles.p + qd->h_list_off[pkl];
+            s.tileq_kl = qd->tiles_q.p + qd->h_list_off[pkl];
             s.nact_ij = e->d_nact.p + pij;
             s.nact_kl = e->d_nact.p + pkl;
             s.ij_begin = ij0;

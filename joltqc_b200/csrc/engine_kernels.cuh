@@ -115,7 +115,6 @@ struct ScreenArgs {
     unsigned* __restrict__ counter;          // queue entries written by this chunk
     unsigned long long* __restrict__ qcount; // quartets that passed (accounting)
     int tile_mode;                           // 1: emit (i, j, k-tile, l-tile, mask16) records for jk_tile16
-    int kl_static;                           // 1: tiles_kl is the static k-major list; test the pair cutoff here
 };
 
 // Thread = (one (i,j) shell pair of an ij tile) x (one kl tile): 16 quartet tests in the
@@ -130,15 +129,8 @@ __global__ void __launch_bounds__(256) screen_tasks_kernel(const ScreenArgs s)
     const int ij_slot = blockIdx.y * 8 + threadIdx.y;
     const int ij_idx = (s.ij_begin + (ij_slot >> 4)) * s.world + s.rank;
     const int pair = ij_slot & 15;
-    bool active = (ij_slot >> 4) < s.ij_count && ij_idx < *s.nact_ij && kl_slot < s.kl_count;
-    if (active) {
-        if (s.kl_static) {   // same set as the active prefix of the q-sorted list (jk.py:185-187, 412)
-            const double pcut = log(1e-13) - (double)ordered_to_float(*s.log_max_ordered);
-            active = (double)s.tileq_kl[s.kl_begin + kl_slot] > pcut;
-        } else {
-            active = (s.kl_begin + kl_slot) < *s.nact_kl;
-        }
-    }
+    bool active = (ij_slot >> 4) < s.ij_count && ij_idx < *s.nact_ij && kl_slot < s.kl_count &&
+                  (s.kl_begin + kl_slot) < *s.nact_kl;
     int ish = 0, jsh = 0, tk = 0, tl = 0;
     float q_ij = 0.f;
     const float log_max = fmaxf(ordered_to_float(*s.log_max_ordered), -36.8f);
@@ -215,33 +207,15 @@ __global__ void __launch_bounds__(256) screen_tasks_kernel(const ScreenArgs s)
         }
         return;
     }
-    // Flat list, k-major within the warp: first every lane's survivors with local k index 0, then
-    // k index 1, ... .  With a k-major tile list all lanes of a warp share the k tile, so runs of up
-    // to 128 consecutive quartets share (i, j, k) and the consumer can combine their J_ij, K_ik and
-    // K_jk contributions in the warp before they reach the L2.
     unsigned base = 0;
     if (lane == 31) base = atomicAdd(s.counter, (unsigned)total);
     base = __shfl_sync(0xffffffffu, base, 31);
-#pragma unroll
-    for (int k = 0; k < TILE; k++) {
-        const unsigned mk = (mask >> (k * TILE)) & 0xFu;
-        const int ck = __popc(mk);
-        int inc = ck;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += n;
-        }
-        const int tot_k = __shfl_sync(0xffffffffu, inc, 31);
-        unsigned pos = base + inc - ck;
-        unsigned m = mk;
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            s.queue[pos++] = make_ushort4((unsigned short)ish, (unsigned short)jsh, (unsigned short)(tk * TILE + k),
-                                          (unsigned short)(tl * TILE + b));
-        }
-        base += tot_k;
+    unsigned pos = base + incl - cnt;
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        s.queue[pos++] = make_ushort4((unsigned short)ish, (unsigned short)jsh,
+                                      (unsigned short)(tk * TILE + (b >> 2)), (unsigned short)(tl * TILE + (b & 3)));
     }
 }
 
