@@ -273,27 +273,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
         poz[s] = CART_Z[LK][pk[s]] * DK + CART_Z[LL][pl[s]] * DL + 2 * GS;
     }
 
-    // the quartet of the next batch is fetched one batch ahead and its shell records prefetched
-    const unsigned bstep = gridDim.x * NWARPS;
-    ushort4 sq_next = make_ushort4(0, 0, 0, 0);
-    {
-        const unsigned t0 = (blockIdx.x * NWARPS + warp) * QPW + grp;
-        if (lane_ok && t0 < ntasks) sq_next = a.quartets[t0];
-    }
 #pragma unroll 1
-    for (unsigned batch = blockIdx.x * NWARPS + warp; batch < nbatch; batch += bstep) {
+    for (unsigned batch = blockIdx.x * NWARPS + warp; batch < nbatch; batch += gridDim.x * NWARPS) {
         const unsigned task = batch * QPW + grp;
         const bool active = lane_ok && task < ntasks;
-        const ushort4 sq = sq_next;
-        {
-            const unsigned tn = (batch + bstep) * QPW + grp;
-            if (lane_ok && tn < ntasks) {
-                sq_next = a.quartets[tn];
-                if (t < 4) prefetch_l1(a.basis + (t == 0 ? sq_next.x : t == 1 ? sq_next.y : t == 2 ? sq_next.z : sq_next.w) * BASIS_STRIDE);
-            } else {
-                sq_next = make_ushort4(0, 0, 0, 0);
-            }
-        }
+        const ushort4 sq = active ? a.quartets[task] : make_ushort4(0, 0, 0, 0);
         const int ish = sq.x, jsh = sq.y, ksh = sq.z, lsh = sq.w;
         const double* __restrict__ bi = a.basis + ish * BASIS_STRIDE;
         const double* __restrict__ bj = a.basis + jsh * BASIS_STRIDE;

@@ -59,9 +59,6 @@ __device__ constexpr signed char CART_Z[5][15] = {
     {0,0,1,0,1,2,0,1,2,3,0,0,0,0,0},
     {0,0,1,0,1,2,0,1,2,3,0,1,2,3,4}};
 
-// Non-binding L1 prefetch of the line holding p (no destination register).
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 // Packed record: [x, y, z, ao_loc, c0, e0, c1, e1, c2, e2, 0, 0]
 struct ShellHead {
     double x, y, z, ao;
