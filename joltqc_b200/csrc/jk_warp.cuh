@@ -508,37 +508,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
                 // flush when the last pass has been staged (for n_dm > 1 every pass flushes its share)
                 if (pass == NPASS - 1 || per_pass_flush) {
                     __syncwarp();
-                    const bool partial_j = per_pass_flush;   // then only this pass' j range is valid
-                    const int jlo = partial_j ? jc0 : 0, jhi = partial_j ? jc0 + NJC : NFJ;
-                    if constexpr (DO_J && QPW > 1) {
-                        // J_ij: the quartet groups of a warp usually share (i,j) (the task list comes in
-                        // (i,j) runs), so their sums are combined across groups with shuffles and only
-                        // the first group of a run issues the reduction (same-address FP64 atomics
-                        // serialise in the L2).  Warp-uniform code: every lane executes the shuffles.
-                        double* __restrict__ vj = a.vj + b * nao2;
-                        const unsigned key = active ? (((unsigned)ish << 16) | (unsigned)jsh) : (0xFFFF0000u | (unsigned)lane);
-                        const unsigned key_prev = __shfl_up_sync(0xffffffffu, key, T);
-                        const bool leader = (grp == 0) || (key_prev != key);
-#pragma unroll
-                        for (int m = 0; m < (NIJ + T - 1) / T; m++) {
-                            const int e = t + m * T;
-                            const int r = e / NFI, c = e - r * NFI;
-                            const bool valid = active && e < NIJ && r >= jlo && r < jhi;
-                            double v = 0.0;
-                            if (valid) {
-#pragma unroll
-                                for (int u = 0; u < T; u++) v += s_st[ST_IJ + u * NIJ + e];
-                            }
-#pragma unroll
-                            for (int d = 1; d < QPW; d <<= 1) {
-                                const double o = __shfl_down_sync(0xffffffffu, v, d * T);
-                                const unsigned k2 = __shfl_down_sync(0xffffffffu, key, d * T);
-                                if (grp + d < QPW && k2 == key) v += o;
-                            }
-                            if (valid && leader) atomicAdd(vj + (size_t)(j0 + r) * nao + i0 + c, v);
-                        }
-                    }
                     if (active) {
+                        const bool partial_j = per_pass_flush;   // then only this pass' j range is valid
+                        const int jlo = partial_j ? jc0 : 0, jhi = partial_j ? jc0 + NJC : NFJ;
 // lanes of the group tile a block as (RT rows) x (CW columns); rows/columns advance by compile-time
 // steps so that every address is one base plus immediates (no per-element division)
 #define JQC_FLUSH(NR, NC, RLO, RHI, EXPR, DEST)                                                    \
@@ -565,11 +537,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS *
     }
                         if constexpr (DO_J) {
                             double* __restrict__ vj = a.vj + b * nao2;
-                            if constexpr (QPW == 1) {
-                                JQC_FLUSH(NFJ, NFI, jlo, jhi,
-                                          _Pragma("unroll") for (int u = 0; u < T; u++) v += s_st[ST_IJ + u * NIJ + r * NFI + c],
-                                          vj + (size_t)(j0 + r) * nao + i0 + c)
-                            }
+                            JQC_FLUSH(NFJ, NFI, jlo, jhi,
+                                      _Pragma("unroll") for (int u = 0; u < T; u++) v += s_st[ST_IJ + u * NIJ + r * NFI + c],
+                                      vj + (size_t)(j0 + r) * nao + i0 + c)
                             if (NPASS > 1 && !per_pass_flush) {
 #pragma unroll
                                 for (int s = 0; s < NKLP; s++)
