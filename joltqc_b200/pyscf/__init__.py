@@ -4,8 +4,8 @@ Same entry point and semantics as ``jqc.pyscf.apply`` (jqc/pyscf/__init__.py:121
 Coulomb/exchange path: it patches ``get_jk / get_j / get_k / get_veff / reset / as_scanner``
 on a GPU4PySCF-style RHF/RKS object in place and returns it.  The DFT-grid kernels the
 reference also patches on RKS objects (get_rho, nr_rks, nr_nlc_vxc) are out of scope here and
-left to the host package; for RKS objects ``get_veff`` is not replaced either (the stock
-GPU4PySCF ``get_veff`` already calls the patched ``get_jk/get_j/get_k``).
+left to the host package; the RKS ``get_veff`` glue that decides which density reaches
+``get_jk/get_j/get_k`` (jqc/pyscf/rks.py:180-262) is provided by ``joltqc_b200.pyscf.rks``.
 """
 from functools import wraps
 from types import MethodType
@@ -80,7 +80,10 @@ def apply(obj, config: Optional[Dict[str, Any]] = None):
             obj.get_j = _jk.generate_get_j(layout, cutoff_fp64=cutoff_fp64, cutoff_fp32=cutoff_fp32)
         if hasattr(obj, "get_k"):
             obj.get_k = _jk.generate_get_k(layout, cutoff_fp64=cutoff_fp64, cutoff_fp32=cutoff_fp32)
-        if obj.istype("RHF") and not obj.istype("RKS"):
+        if obj.istype("RKS"):
+            from . import rks as _rks
+            obj.get_veff = MethodType(_rks.generate_get_veff(), obj)
+        elif obj.istype("RHF"):
             obj.get_veff = MethodType(_jk.generate_get_veff(), obj)
         obj._jqc_layout = layout
 
