@@ -187,3 +187,62 @@ def test_apply_reset_and_errors(torch_cuda):
     assert abs(e1 - e2) > 1e-6
     with pytest.raises(ValueError):
         mf2.get_jk(mol2, np.zeros((3, 3)))
+
+
+def test_shards_sum_to_full_build(torch_cuda):
+    """jqc_engine_set_shard / jqc_build_partial / jqc_finalize on ONE GPU: the partial [J||K]
+    buffers of rank 0..2 of a world of 3, summed on the device (what the NCCL all_reduce does),
+    finalise to the same J and K as the unsharded build."""
+    import ctypes
+    import torch
+    from joltqc_b200.backend import lib as _lib
+    from joltqc_b200.backend.engine import JKEngine, _wrap_device_buffer
+    mol, lay = make(benzene(), "def2-svp")
+    dm = random_dm(mol.nao, 5)
+    full_j, full_k = lay.engine().get_jk(dm, hermi=1)
+    eng = JKEngine(lay)
+    d3 = torch.as_tensor(dm, device=eng.device).reshape(1, mol.nao, mol.nao).contiguous()
+    total = None
+    counts = 0
+    for rank in range(3):
+        eng.set_shard(rank, 3)
+        p, ln = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.check(eng.L.jqc_build_partial(eng.h, d3.data_ptr(), 1, 1, 1, 1, 0.0, 1e-13, 1e-13, ctypes.byref(p),
+                                           ctypes.byref(ln), None))
+        buf = _wrap_device_buffer(p.value, ln.value, eng.device)
+        torch.cuda.synchronize()
+        counts += int(eng.last_stats()[0].sum())
+        total = buf.clone() if total is None else total + buf
+    buf.copy_(total)                       # stand-in for all_reduce(SUM) into the engine's buffer
+    vj, vk = torch.empty_like(d3), torch.empty_like(d3)
+    _lib.check(eng.L.jqc_finalize(eng.h, vj.data_ptr(), vk.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert (vj[0] - full_j).abs().max().item() < 1e-11 * full_j.abs().max().item()
+    assert (vk[0] - full_k).abs().max().item() < 1e-11 * full_k.abs().max().item()
+    assert counts == int(lay.engine().last_stats()[0].sum())      # every quartet exactly once
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomized_parity(torch_cuda, seed):
+    """random small molecules / bases / densities / options against the oracle"""
+    rng = np.random.RandomState(100 + seed)
+    elems = ["H", "C", "N", "O"]
+    basis = ["sto-3g", "def2-svp", "def2-tzvp", "def2-tzvpp"][rng.randint(4)]
+    natm = rng.randint(2, 5)
+    atom = [(elems[rng.randint(4)], tuple(rng.uniform(-2.2, 2.2, 3))) for _ in range(natm)]
+    # keep atoms apart
+    xyz = np.array([a[1] for a in atom])
+    for a in range(natm):
+        for b in range(a):
+            if np.linalg.norm(xyz[a] - xyz[b]) < 0.7:
+                xyz[a] += 1.5
+    atom = [(atom[a][0], tuple(xyz[a])) for a in range(natm)]
+    cart = bool(rng.randint(2))
+    mol, lay = make(atom, basis, cart=cart)
+    hermi = int(rng.randint(2))
+    n = None if rng.randint(2) else 2
+    dm = random_dm(mol.nao, 200 + seed, n=n, symmetric=bool(hermi))
+    omega = None if rng.randint(3) else 0.3
+    with_j, with_k = [(True, True), (True, False), (False, True)][rng.randint(3)]
+    cutoff = [1e-13, 1e-10][rng.randint(2)]
+    _check(lay, dm, hermi=hermi, with_j=with_j, with_k=with_k, omega=omega, cutoff=cutoff)
