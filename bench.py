@@ -223,6 +223,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # keep stdout to the single JSON line: NCCL prints its version banner there at this level
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = lay.engine()
     if world > 1:
