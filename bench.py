@@ -164,7 +164,25 @@ def cpu_port_baseline(lay, dm, budget_s=20.0):
             "counts": orc.last_counts.copy()}
 
 
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Route fd 1 to stderr for the whole run (NCCL and other native libraries print banners on
+    stdout) and keep the original stdout for the single JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -213,7 +231,7 @@ def main():
                                  "sample": f"every {res['stride']}th (ij) shell pair of the same build "
                                            f"({res['quartets_sample']} quartets in {np.median(ts):.2f} s), extrapolated x{res['stride']}"},
                 "e2e": {"value": est, "unit": "s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     import torch
@@ -223,9 +241,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # keep stdout to the single JSON line: NCCL prints its version banner there at this level
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = lay.engine()
     if world > 1:
@@ -362,7 +377,7 @@ def main():
         line["cpu_baseline"] = {"value": est, "unit": "s/iter", "cores": res["cores"], "kind": "port",
                                 "sample": f"every {res['stride']}th (ij) shell pair of the same build "
                                           f"({res['quartets_sample']} quartets in {res['seconds_sample']:.2f} s), extrapolated x{res['stride']}"}
-    print(json.dumps(line))
+    _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
