@@ -30,7 +30,13 @@ def _run(cmd):
     return r.stderr
 
 
-def build(force=False, verbose=False, jobs=None):
+def build(force=False, verbose=False, jobs=None, extra_flags=None):
+    """extra_flags: e.g. ["-DJQC_WARP_FORCE_ACC=40", "-DJQC_WARP_FORCE_REGS=168"] for a tuning build
+    (forces a full rebuild; see tools/tune_warp.py)."""
+    global FLAGS
+    if extra_flags:
+        FLAGS = FLAGS + list(extra_flags)
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     stamp = _newest_src()
     todo = []
@@ -57,4 +63,4 @@ def build(force=False, verbose=False, jobs=None):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))

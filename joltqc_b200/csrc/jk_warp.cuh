@@ -136,10 +136,28 @@ __host__ __device__ constexpr bool use_2d_map(int NR, int NC, int T)
 }
 
 // ---- per-class lane layout ---------------------------------------------------------------
-constexpr int WARP_ACC_MAX = 60;   // doubles of (i,j)-block accumulators per lane
+// Per-class tuning of the multi-lane kernel (the counterpart of the reference's per-device fragment
+// tables, jqc/backend/data/optimal_scheme_*.json): ACC = accumulator doubles per lane (decides how
+// many lanes share a quartet), REGS = register budget (255 -> 8 warps/SM, 168 -> 12 warps/SM).
+// jk_warp_tuning.h is generated by tools/tune_warp.py from measured per-class times on B200; a whole
+// build can be forced to one variant with -DJQC_WARP_FORCE_ACC=.. -DJQC_WARP_FORCE_REGS=..
+template <int LI, int LJ, int LK, int LL>
+struct WarpTune {
+    static constexpr int ACC = 60, REGS = 255;
+};
+#if defined(JQC_WARP_FORCE_ACC) && defined(JQC_WARP_FORCE_REGS)
+#define JQC_TUNE_ACC(LI, LJ, LK, LL) JQC_WARP_FORCE_ACC
+#define JQC_TUNE_REGS(LI, LJ, LK, LL) JQC_WARP_FORCE_REGS
+#else
+#include "jk_warp_tuning.h"
+#define JQC_TUNE_ACC(LI, LJ, LK, LL) (WarpTune<LI, LJ, LK, LL>::ACC)
+#define JQC_TUNE_REGS(LI, LJ, LK, LL) (WarpTune<LI, LJ, LK, LL>::REGS)
+#endif
 
 template <int LI, int LJ, int LK, int LL>
 struct WarpPlan {
+    static constexpr int WARP_ACC_MAX = JQC_TUNE_ACC(LI, LJ, LK, LL);
+    static constexpr int REGS = JQC_TUNE_REGS(LI, LJ, LK, LL);
     using S = QuartetShape<LI, LJ, LK, LL>;
     static constexpr int NIJ = S::NFI * S::NFJ, NKL = S::NFK * S::NFL;
     // bra passes: split the j components so that one pass keeps <= WARP_ACC_MAX accumulators per pair
@@ -224,11 +242,9 @@ struct WarpPlan {
         JQC_STAGE(D_IK, NFI, NFK, i0, k0)              \
     }
 
-#ifndef JQC_WARP_REGS
-#define JQC_WARP_REGS 255   // register budget per thread of the multi-lane kernel (occupancy lever)
-#endif
 template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 65536 / (JQC_WARP_REGS * NWARPS * 32)) jk_warp_kernel(const JKArgs a)
+__global__ void __launch_bounds__(NWARPS * 32, 65536 / (WarpPlan<LI, LJ, LK, LL>::REGS * NWARPS * 32))
+jk_warp_kernel(const JKArgs a)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     using P = WarpPlan<LI, LJ, LK, LL>;
