@@ -37,7 +37,14 @@ struct QuartetShape {
     static constexpr int GSIZE = DL * (LL + 1);
 };
 
-constexpr int JQC_SMALL_N = 81;
+// Blocks up to JQC_SMALL_N integrals run on the register kernel.  81 fit without spilling; up to 108
+// the kernel spills ~1 KB per thread yet still beats the multi-lane kernel by ~2x (measured on B200,
+// profiles/r1/class_times_09_*.csv), hence the higher threshold.  The 4x4-tile variant stays at 81.
+#ifndef JQC_SMALL_N_VALUE
+#define JQC_SMALL_N_VALUE 108
+#endif
+constexpr int JQC_SMALL_N = JQC_SMALL_N_VALUE;
+constexpr int JQC_TILE16_N = 81;
 
 // register-resident variant: blocks of <= 27 integrals fit 128 registers (two CTAs per SM)
 #define JQC_MINB(a, b, c, d) (QuartetShape<a, b, c, d>::N <= 27 ? 2 : 1)

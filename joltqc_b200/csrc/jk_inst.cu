@@ -52,7 +52,7 @@ static cudaError_t launch_one(const JKArgs& a, int nsm, cudaStream_t st)
     }
     constexpr bool SMALL = S::N <= JQC_SMALL_N;
     constexpr int NT = SMALL ? 256 : 128;
-    static_assert(JQC_SMALL_N == 81, "keep jk_uses_tiles() in jk_launch.h in sync");
+    static_assert(JQC_TILE16_N == 81, "keep jk_uses_tiles() in jk_launch.h in sync");
     void (*kern)(const JKArgs);
     if constexpr (SMALL) kern = TILES ? jk_tile16_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>
                                       : jk_1q1t_kernel_small<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
@@ -72,7 +72,7 @@ template <int LK, int LL>
 static cudaError_t launch_variant(int variant, const JKArgs& a, int nsm, cudaStream_t st)
 {
     // bit 2 of the variant selects the tile-record kernel for the small classes
-    constexpr bool SM = QuartetShape<JQC_LI, JQC_LJ, LK, LL>::N <= JQC_SMALL_N;
+    constexpr bool SM = QuartetShape<JQC_LI, JQC_LJ, LK, LL>::N <= JQC_TILE16_N;
     switch (variant) {
         case 3: return launch_one<LK, LL, true, true, false>(a, nsm, st);
         case 1: return launch_one<LK, LL, true, false, false>(a, nsm, st);
