@@ -374,8 +374,11 @@ jk_warp_kernel(const JKArgs a)
                     }
                     const double x = rr * theta * theta_fac;
                     __syncwarp();   // previous product phase has finished reading g
+                    // with one primitive quartet the g arrays of pass 0 are still valid in later bra
+                    // passes (nothing overwrites them): skip the roots and recurrences there
+                    const bool reuse_g = (NPASS > 1) && pass > 0 && (a.npi * a.npj * a.npk * a.npl == 1);
                     // roots: lane t computes roots t, t+T, ...
-                    if (active) {
+                    if (active && !reuse_g) {
 #pragma unroll 1
                         for (int r = t; r < NROOTS; r += T) {
                             double rt, wt;
@@ -386,7 +389,7 @@ jk_warp_kernel(const JKArgs a)
                     }
                     __syncwarp();
                     // recurrences: item = (root, direction)
-                    if (active) {
+                    if (active && !reuse_g) {
 #pragma unroll 1
                         for (int item = t; item < 3 * NROOTS; item += T) {
                             const int r = item / 3, d = item - 3 * r;
