@@ -130,14 +130,34 @@ class JKEngine:
         self.set_shard(rank, world)
         self._world = int(world)
 
-    def build_partial_allreduce(self, d3, hermi, with_j, with_k, om, cutoff_fp64, cutoff_fp32, group=None):
-        import torch.distributed as dist
+    def build_partial(self, dm, hermi=0, with_j=True, with_k=True, omega=None, cutoff_fp64=1e-13, cutoff_fp32=1e-13):
+        """This rank's share of the kernel-side [J || K] buffer (jqc_build_partial): a torch view of
+        engine-owned memory, ready for an all_reduce; follow with finalize()."""
+        d = self._dev(dm)
+        d3 = d.reshape(-1, d.shape[-2], d.shape[-1])
+        self._last_shape = d.shape
         p = ctypes.c_void_p()
         ln = ctypes.c_size_t()
-        _lib.check(self.L.jqc_build_partial(self.h, d3.data_ptr(), d3.shape[0], int(hermi), int(with_j), int(with_k),
-                                            om, float(cutoff_fp64), float(cutoff_fp32), ctypes.byref(p),
-                                            ctypes.byref(ln), self._stream()))
-        buf = _wrap_device_buffer(p.value, ln.value, self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.jqc_build_partial(self.h, d3.data_ptr(), d3.shape[0], int(hermi), int(with_j), int(with_k),
+                                                0.0 if omega is None else float(omega), float(cutoff_fp64),
+                                                float(cutoff_fp32), ctypes.byref(p), ctypes.byref(ln), self._stream()))
+        self._last_jk = (bool(with_j), bool(with_k), d3.shape)
+        return _wrap_device_buffer(p.value, ln.value, self.device)
+
+    def finalize(self):
+        """Post-processing + back-transform of the (reduced) partial buffer (jqc_finalize)."""
+        with_j, with_k, shape3 = self._last_jk
+        vj = torch.empty(shape3, dtype=torch.float64, device=self.device) if with_j else None
+        vk = torch.empty(shape3, dtype=torch.float64, device=self.device) if with_k else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.jqc_finalize(self.h, vj.data_ptr() if with_j else None, vk.data_ptr() if with_k else None,
+                                           self._stream()))
+        return (vj.reshape(self._last_shape) if with_j else 0), (vk.reshape(self._last_shape) if with_k else 0)
+
+    def build_partial_allreduce(self, d3, hermi, with_j, with_k, om, cutoff_fp64, cutoff_fp32, group=None):
+        import torch.distributed as dist
+        buf = self.build_partial(d3, hermi, with_j, with_k, om, cutoff_fp64, cutoff_fp32)
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         return buf
 

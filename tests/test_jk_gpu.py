@@ -246,3 +246,15 @@ def test_randomized_parity(torch_cuda, seed):
     with_j, with_k = [(True, True), (True, False), (False, True)][rng.randint(3)]
     cutoff = [1e-13, 1e-10][rng.randint(2)]
     _check(lay, dm, hermi=hermi, with_j=with_j, with_k=with_k, omega=omega, cutoff=cutoff)
+
+
+def test_python_partial_finalize_api(torch_cuda):
+    """JKEngine.build_partial / finalize (the two-phase multi-GPU API) on a single rank"""
+    mol, lay = make(H2O, "def2-svp")
+    dm = random_dm(mol.nao, 8)
+    eng = lay.engine()
+    ref_j, ref_k = eng.get_jk(dm, hermi=1)
+    buf = eng.build_partial(dm, hermi=1)
+    assert buf.numel() == 2 * lay.nao * lay.nao
+    vj, vk = eng.finalize()
+    assert (vj - ref_j).abs().max().item() < 1e-11 and (vk - ref_k).abs().max().item() < 1e-11
