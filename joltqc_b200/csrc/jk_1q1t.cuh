@@ -6,9 +6,10 @@
 //     from device memory (no host round trip between task generation and evaluation);
 //   * primitive counts are run-time loop bounds (one instantiation per angular class);
 //   * Rys roots from the interval table without small-x / erf branches;
-//   * blocks of up to JQC_SMALL_N integrals are fully unrolled into registers (_small); larger
-//     blocks run the same code rolled with thread-local scratch (_large), which is correct for
-//     every l <= 4 and is the baseline the tuned multi-lane kernels replace.
+//   * blocks of up to JQC_SMALL_N integrals are fully unrolled into registers (_small), with the
+//     J_ij contributions of a warp that shares (i,j) combined by shuffles before one reduction;
+//     larger blocks run on jk_warp.cuh, and the same body rolled with thread-local scratch
+//     (_large) is the any-l fallback (used for classes with g shells in the bra).
 #pragma once
 #include "jqc_common.cuh"
 

@@ -12,8 +12,9 @@ JQC_DECL(3, 0) JQC_DECL(3, 1) JQC_DECL(3, 2) JQC_DECL(3, 3)
 JQC_DECL(4, 0) JQC_DECL(4, 1) JQC_DECL(4, 2) JQC_DECL(4, 3) JQC_DECL(4, 4)
 #undef JQC_DECL
 
-// Classes whose blocks fit in one thread's registers are fed (i, j, k-tile, l-tile, mask) records
-// (jk_tile16.cuh); everything else consumes flat ushort4 quartet lists.
+// Classes of <= 81 integrals can optionally be fed (i, j, k-tile, l-tile, mask) records and run on
+// jk_tile16.cuh (engine option JQC_SMALL_TILES=1); by default every class consumes flat ushort4
+// quartet lists (register kernel up to 108 integrals, multi-lane kernel above).
 inline bool jk_uses_tiles(int li, int lj, int lk, int ll)
 {
     auto nf = [](int l) { return (l + 1) * (l + 2) / 2; };
