@@ -19,7 +19,7 @@
 
 #include "../../include/joltqc_b200.h"
 #include "engine_kernels.cuh"
-#include "jk_1q1t.cuh"
+#include "jk_brick.cuh"
 #include "jk_launch.h"
 
 using namespace jqc;
@@ -39,7 +39,7 @@ static int fail(int code, const std::string& msg)
 
 namespace {
 
-constexpr size_t QUEUE_CAP = size_t(1) << 27;   // ushort4 entries (1 GiB), allocated once
+constexpr size_t QUEUE_CAP = size_t(1) << 27;   // ushort4 entries (1 GiB) at most, allocated on first use
 constexpr int MAX_CHUNKS = 1 << 18;
 
 template <class T>
@@ -70,6 +70,17 @@ struct QData {                    // per-omega Schwarz data
     DevBuf<float> tiles_q;
     DevBuf<int> list_off;         // npairs + 1
     std::vector<int> h_list_off;
+    // shell-pair lists of the brick kernel (jk_brick.cuh), one segment per group pair (ga >= gb):
+    //   ket role: pairs ordered by (bucket of 32 shells of ga, q descending) -> 32 neighbours = one brick
+    //   bra role: for every shell a of ga its partners b, q descending (CSR)
+    DevBuf<ushort2> kl;
+    DevBuf<float> kl_q, kl_tq;
+    DevBuf<unsigned short> j_idx;
+    DevBuf<float> j_q, j_tq;
+    DevBuf<int> j_off;            // per group pair: (size of ga) + 1 offsets, absolute into j_idx
+    std::vector<int> h_pair_off;  // npairs + 1: segment of each group pair in kl / j_idx
+    std::vector<int> h_joff_off;  // npairs: start of each group pair's row offsets in j_off
+    std::vector<float> h_qmax;    // npairs: largest q of the group pair
 };
 
 struct ChunkRec { int key; long long pw; };   // class key and primitive weight of a launch
@@ -98,6 +109,14 @@ struct jqc_engine {
     // task format for blocks of <= 81 integrals: 0 flat quartets (default), 1 4x4 tile records.
     // Both were measured in round 1 (profiles/README.md); JQC_SMALL_TILES=1 selects the tile kernel.
     int small_tiles = 0;
+    // brick kernel (jk_brick.cuh) for the classes of <= 108 integrals and one density matrix;
+    // JQC_BRICK=0 falls back to the quartet-list kernels (kept as the cross-check of the tests)
+    int use_brick = 1;
+    int brick_ichunk = 8;
+    // chunking of the quartet-list path; JQC_QUEUE_CAP / JQC_KL_CHUNK shrink them so that small test
+    // molecules exercise the multi-chunk loops
+    size_t queue_cap = QUEUE_CAP;
+    int kl_chunk_max = 2048;
     // state of the last build
     int last_n = 0, last_neff = 0, last_hermi = 1, last_j = 0, last_k = 0, launches = 0;
     bool built = false, profiling = false;
@@ -114,8 +133,9 @@ extern "C" const char* jqc_last_error(void) { return g_err.c_str(); }
 extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine** out)
 {
     if (!d || !out) return fail(JQC_EINVAL, "null argument");
-    if (d->nbas <= 0 || d->nbas % JQC_TILE || d->nbas > 65535)
-        return fail(JQC_EINVAL, "nbas must be a positive multiple of 4 and <= 65535");
+    // 56 K shells: ushort shell indices and one float per shell of dynamic shared memory in dm_pool_kernel
+    if (d->nbas <= 0 || d->nbas % JQC_TILE || d->nbas > 56 * 1024)
+        return fail(JQC_EINVAL, "nbas must be a positive multiple of 4 and <= 57344");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(JQC_ECUDA, "no CUDA device: joltqc_b200 has no CPU fallback");
@@ -124,6 +144,10 @@ extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine
     std::unique_ptr<jqc_engine> e(new jqc_engine);
     e->device = device;
     if (const char* m = getenv("JQC_SMALL_TILES")) e->small_tiles = atoi(m) != 0;
+    if (const char* m = getenv("JQC_BRICK")) e->use_brick = atoi(m) != 0;
+    if (const char* m = getenv("JQC_BRICK_ICHUNK")) e->brick_ichunk = std::max(1, atoi(m));
+    if (const char* m = getenv("JQC_QUEUE_CAP")) e->queue_cap = std::min<size_t>(QUEUE_CAP, std::max<size_t>(256, (size_t)atoll(m)));
+    if (const char* m = getenv("JQC_KL_CHUNK")) e->kl_chunk_max = std::max(1, atoi(m));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     e->nsm = prop.multiProcessorCount;
@@ -217,6 +241,8 @@ extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine
     CU(e->d_molao_m.upload(molao_m));
     CU(e->d_child_ptr.upload(cptr));
     CU(e->d_child_list.upload(clist));
+    if ((size_t)d->nbas * sizeof(float) > 48 * 1024)   // dm_pool_kernel keeps one row of shell maxima in shared memory
+        CU(cudaFuncSetAttribute(dm_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(d->nbas * sizeof(float))));
     CU(e->d_logmax.ensure(1));
     CU(e->d_nact.ensure(e->npairs()));
     CU(e->d_counters.ensure(MAX_CHUNKS));
@@ -262,7 +288,10 @@ static int get_qdata(jqc_engine* e, double omega, QData** out)
     {
         const int nfm = (e->lmax + 1) * (e->lmax + 2) / 2;
         const int blk = nfm * nfm * nfm * nfm;
-        const int threads = 64, blocks = std::max(1, std::min(e->nsm * 2, (nbas * (nbas + 1) / 2 + threads - 1) / threads));
+        // scratch = one integral block per resident thread: bounded to ~1 GiB (g shells: 405 KB per thread)
+        const int threads = 64;
+        int blocks = std::max(1, std::min(e->nsm * 2, (nbas * (nbas + 1) / 2 + threads - 1) / threads));
+        blocks = std::max(1, std::min(blocks, (int)((size_t(1) << 30) / ((size_t)threads * blk * sizeof(double)))));
         DevBuf<GenScratch> scratch;
         DevBuf<double> blocksbuf;
         CU(scratch.ensure((size_t)threads * blocks));
@@ -299,6 +328,62 @@ static int get_qdata(jqc_engine* e, double omega, QData** out)
     CU(qd->tiles.upload(tiles));
     CU(qd->tiles_q.upload(tiles_q));
     CU(qd->list_off.upload(qd->h_list_off));
+    {   // pair lists for the brick kernel
+        std::vector<float> hq((size_t)nbas * nbas);
+        CU(cudaMemcpy(hq.data(), qd->q.p, hq.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        std::vector<ushort2> kl;
+        std::vector<float> kl_q, kl_tq, j_q, j_tq;
+        std::vector<unsigned short> j_idx;
+        std::vector<int> j_off;
+        qd->h_pair_off.assign(1, 0);
+        struct Ent { int bucket; float q; unsigned short a, b; };
+        std::vector<Ent> v;
+        for (int ga = 0; ga < e->ngroups; ga++)
+            for (int gb = 0; gb <= ga; gb++) {
+                v.clear();
+                float qmax = -INFINITY;
+                qd->h_joff_off.push_back((int)j_off.size());
+                for (int a = e->goff[ga]; a < e->goff[ga + 1]; a++) {
+                    j_off.push_back((int)j_idx.size());
+                    const size_t row0 = v.size();
+                    const int bend = ga == gb ? a + 1 : e->goff[gb + 1];
+                    for (int b = e->goff[gb]; b < bend; b++) {
+                        const float qv = hq[(size_t)a * nbas + b];
+                        if (!(qv > -90.f)) continue;
+                        v.push_back({(a - e->goff[ga]) / 32, qv, (unsigned short)a, (unsigned short)b});
+                        qmax = std::max(qmax, qv);
+                    }
+                    // bra role: this row by q descending (ties by shell index: deterministic)
+                    std::vector<Ent> row(v.begin() + row0, v.end());
+                    std::sort(row.begin(), row.end(), [](const Ent& x, const Ent& y) { return x.q != y.q ? x.q > y.q : x.b < y.b; });
+                    for (auto& r : row) {
+                        j_idx.push_back(r.b);
+                        j_q.push_back(r.q);
+                        j_tq.push_back(h_tq[(size_t)(r.a / JQC_TILE) * nt + r.b / JQC_TILE]);
+                    }
+                }
+                j_off.push_back((int)j_idx.size());
+                std::sort(v.begin(), v.end(), [](const Ent& x, const Ent& y) {
+                    if (x.bucket != y.bucket) return x.bucket < y.bucket;
+                    if (x.q != y.q) return x.q > y.q;
+                    return x.a != y.a ? x.a < y.a : x.b < y.b;
+                });
+                for (auto& r : v) {
+                    kl.push_back(make_ushort2(r.a, r.b));
+                    kl_q.push_back(r.q);
+                    kl_tq.push_back(h_tq[(size_t)(r.a / JQC_TILE) * nt + r.b / JQC_TILE]);
+                }
+                qd->h_pair_off.push_back((int)kl.size());
+                qd->h_qmax.push_back(qmax);
+            }
+        CU(qd->kl.upload(kl));
+        CU(qd->kl_q.upload(kl_q));
+        CU(qd->kl_tq.upload(kl_tq));
+        CU(qd->j_idx.upload(j_idx));
+        CU(qd->j_q.upload(j_q));
+        CU(qd->j_tq.upload(j_tq));
+        CU(qd->j_off.upload(j_off));
+    }
     *out = qd.get();
     e->qcache[omega] = std::move(qd);
     return JQC_OK;
@@ -320,7 +405,7 @@ extern "C" int jqc_q_matrix(jqc_engine* e, double omega, const float** q_dev)
 static int launch_from_mol(jqc_engine* e, const double* mol, int n, double* kern, bool transpose, cudaStream_t st)
 {
     if (e->nao == 0 || n == 0) return JQC_OK;
-    dim3 grid((e->nao + 127) / 128, e->nao, n);
+    dim3 grid(e->nao, (e->nao + 127) / 128, n);   // rows on grid.x (no 65535 limit)
     dm_from_mol_kernel<<<grid, 128, 0, st>>>(mol, e->mol_nao, kern, e->nao, e->d_ao2shell.p, e->d_ao_loc.p,
                                             e->d_angs.p, e->d_mol_off.p, e->xt, transpose ? 1 : 0);
     CU(cudaGetLastError());
@@ -330,7 +415,7 @@ static int launch_from_mol(jqc_engine* e, const double* mol, int n, double* kern
 static int launch_to_mol(jqc_engine* e, const double* kern, int n, int n_half, int mode, double* mol, cudaStream_t st)
 {
     if (e->mol_nao == 0 || n == 0) return JQC_OK;
-    dim3 grid((e->mol_nao + 127) / 128, e->mol_nao, n);
+    dim3 grid(e->mol_nao, (e->mol_nao + 127) / 128, n);
     dm_to_mol_kernel<<<grid, 128, 0, st>>>(kern, e->nao, n_half, mode, mol, e->mol_nao, e->d_molao_parent.p,
                                           e->d_molao_m.p, e->d_child_ptr.p, e->d_child_list.p, e->d_ao_loc.p,
                                           e->d_angs.p, e->xt);
@@ -375,7 +460,6 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
     CU(e->d_vjk.ensure(std::max<size_t>(2 * neff * nao2, 1)));
     CU(e->d_cond.ensure((size_t)nbas * nbas));
     CU(e->d_logd.ensure((size_t)nbas * nbas));
-    CU(e->d_queue.ensure(QUEUE_CAP));
 
     // 1. AO transform in (+ transposed copies when hermi != 1, jk.py:189-192)
     rc = launch_from_mol(e, dm_dev, n_dm, e->d_dm.p, false, st);
@@ -391,7 +475,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
     {
         const int neg_inf_ordered = (int)0xFF800000 ^ 0x7FFFFFFF;   // float_to_ordered(-inf)
         CU(cudaMemcpyAsync(e->d_logmax.p, &neg_inf_ordered, sizeof(int), cudaMemcpyHostToDevice, st));
-        dim3 grid((nbas + 127) / 128, nbas);
+        dim3 grid(nbas, (nbas + 127) / 128);
         dm_log_kernel<<<grid, 128, 0, st>>>(e->d_cond.p, nbas, hermi == 1 ? 1 : 0, e->d_logd.p, e->d_logmax.p);
         CU(cudaGetLastError());
     }
@@ -418,6 +502,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
     e->chunks.clear();
     e->launches = 0;
     size_t nev = 0;
+    bool queue_ready = false;
     for (int gi = e->ngroups - 1; gi >= 0; gi--)
     for (int gj = gi; gj >= 0; gj--)
     for (int gk = gi; gk >= 0; gk--)
@@ -426,15 +511,65 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
         const int n_ij_all = nact[pij];
         const int n_kl = nact[pkl];
         if (n_ij_all == 0 || n_kl == 0) continue;
-        // this rank owns list entries rank, rank + world, ... of the ij list
-        const int n_ij = (n_ij_all - e->rank + e->world - 1) / e->world;
-        if (n_ij <= 0) continue;
         const int li = e->gl[gi], lj = e->gl[gj], lk = e->gl[gk], ll = e->gl[gl];
         const int key = ((li * 5 + lj) * 5 + lk) * 5 + ll;
         const long long pw = (long long)e->gnp[gi] * e->gnp[gj] * e->gnp[gk] * e->gnp[gl];
-        // chunk so that 256 * ij_tiles * kl_tiles <= QUEUE_CAP
-        const int kl_chunk = std::min(n_kl, 2048);
-        const int ij_chunk = std::max(1, (int)std::min<size_t>(n_ij, QUEUE_CAP / 256 / kl_chunk));
+        if (e->use_brick && neff == 1 && !e->small_tiles && jk_brick_supported(li, lj, lk, ll)) {
+            const int n_kl_pairs = qd->h_pair_off[pkl + 1] - qd->h_pair_off[pkl];
+            const int n_ij_pairs = qd->h_pair_off[pij + 1] - qd->h_pair_off[pij];
+            if (n_kl_pairs == 0 || n_ij_pairs == 0) continue;
+            if ((int)e->chunks.size() >= MAX_CHUNKS) return fail(JQC_ENOMEM, "too many task chunks");
+            const int cid = (int)e->chunks.size();
+            BrickArgs b;
+            b.nao = nao; b.nbas = nbas;
+            b.npi = e->gnp[gi]; b.npj = e->gnp[gj]; b.npk = e->gnp[gk]; b.npl = e->gnp[gl];
+            b.basis = e->d_basis.p; b.dm = e->d_dm.p; b.vj = vj; b.vk = vk; b.omega = omega;
+            b.logd = e->d_logd.p; b.log_max_ordered = e->d_logmax.p; b.cutoff = log_cut;
+            b.kl = qd->kl.p + qd->h_pair_off[pkl];
+            b.kl_q = qd->kl_q.p + qd->h_pair_off[pkl];
+            b.kl_tq = qd->kl_tq.p + qd->h_pair_off[pkl];
+            b.n_kl = n_kl_pairs;
+            b.i_first = e->goff[gi];
+            b.i_count = e->goff[gi + 1] - e->goff[gi];
+            b.j_off = qd->j_off.p + qd->h_joff_off[pij];
+            b.j_idx = qd->j_idx.p; b.j_q = qd->j_q.p; b.j_tq = qd->j_tq.p;
+            b.qmax_ij = qd->h_qmax[pij];
+            b.tri = gi == gk;
+            b.n_blk = (n_kl_pairs + 31) / 32;
+            // bra chunk: 8 shells per task, fewer when the launch would not fill the GPU otherwise
+            {
+                const long long want = 4LL * e->nsm * 16 * e->world;
+                int ic = e->brick_ichunk;
+                while (ic > 1 && (long long)b.n_blk * ((b.i_count + ic - 1) / ic) < want) ic >>= 1;
+                b.ichunk = ic;
+            }
+            b.n_ichunk = (b.i_count + b.ichunk - 1) / b.ichunk;
+            b.rank = e->rank; b.world = e->world;
+            b.work = e->d_counters.p + cid;
+            b.qcount = e->d_qcounts.p + cid;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (e->profiling) {
+                while (e->ev.size() < nev + 2) { cudaEvent_t x; CU(cudaEventCreate(&x)); e->ev.push_back(x); }
+                e0 = e->ev[nev++]; e1 = e->ev[nev++];
+                CU(cudaEventRecord(e0, st));
+            }
+            CU(jk_brick_launch(li, lj, lk, ll, variant, b, e->nsm, st));
+            if (e->profiling) CU(cudaEventRecord(e1, st));
+            e->launches += 1;
+            e->chunks.push_back({key, pw});
+            continue;
+        }
+        // quartet-list path: this rank owns list entries rank, rank + world, ... of the ij tile list
+        const int n_ij = (n_ij_all - e->rank + e->world - 1) / e->world;
+        if (n_ij <= 0) continue;
+        // chunk so that 256 * ij_tiles * kl_tiles <= queue capacity (and the grid's y extent <= 65535)
+        const int kl_chunk = std::min({n_kl, e->kl_chunk_max, (int)(e->queue_cap / 256)});
+        const int ij_chunk = std::max(1, (int)std::min<size_t>({(size_t)n_ij, e->queue_cap / 256 / kl_chunk, (size_t)32767}));
+        if (!queue_ready) {   // sized once per build from the longest active tile list
+            const size_t mx = (size_t)*std::max_element(nact.begin(), nact.end());
+            CU(e->d_queue.ensure(std::max<size_t>(256, std::min(e->queue_cap, 256 * mx * std::min<size_t>(mx, e->kl_chunk_max)))));
+            queue_ready = true;
+        }
         for (int ij0 = 0; ij0 < n_ij; ij0 += ij_chunk)
         for (int kl0 = 0; kl0 < n_kl; kl0 += kl_chunk) {
             if ((int)e->chunks.size() >= MAX_CHUNKS) return fail(JQC_ENOMEM, "too many task chunks");

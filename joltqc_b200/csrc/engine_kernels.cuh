@@ -7,14 +7,6 @@
 
 namespace jqc {
 
-// ------------------------------------------------------------------ ordered float <-> int
-__device__ __forceinline__ int float_to_ordered(float f)
-{
-    int i = __float_as_int(f);
-    return i >= 0 ? i : i ^ 0x7FFFFFFF;
-}
-__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
-
 // ------------------------------------------------------------------ density pooling
 // dm_cond[I,J] = max_b max_{mu in I, nu in J} |float(D_b[mu,nu])|  (reference:
 // max_block_pooling, jqc/backend/linalg_helper.py:125-211, on the fp32 copy jk.py:172-173).
@@ -47,8 +39,8 @@ __global__ void dm_pool_kernel(const double* __restrict__ dm, int n_dm, int nao,
 __global__ void dm_log_kernel(const float* __restrict__ cond, int nbas, int hermi, float* __restrict__ logc,
                               int* __restrict__ log_max_ordered)
 {
-    const int J = blockIdx.x * blockDim.x + threadIdx.x;
-    const int I = blockIdx.y;
+    const int J = blockIdx.y * blockDim.x + threadIdx.x;
+    const int I = blockIdx.x;
     float lg = -CUDART_INF_F;
     if (J < nbas) {
         float v = cond[(size_t)I * nbas + J];
@@ -156,7 +148,7 @@ __global__ void __launch_bounds__(256) screen_tasks_kernel(const ScreenArgs s)
         const float dik[4] = {d_ik.x, d_ik.y, d_ik.z, d_ik.w}, djk[4] = {d_jk.x, d_jk.y, d_jk.z, d_jk.w};
         const float dil[4] = {d_il.x, d_il.y, d_il.z, d_il.w}, djl[4] = {d_jl.x, d_jl.y, d_jl.z, d_jl.w};
         const float d_ij = s.logd[(size_t)ish * nbas + jsh];
-        const int bas_ij = ish * nbas + jsh;
+        const long long bas_ij = (long long)ish * nbas + jsh;
 #pragma unroll
         for (int k = 0; k < TILE; k++) {
             const int ksh = ksh0 + k;
@@ -166,7 +158,7 @@ __global__ void __launch_bounds__(256) screen_tasks_kernel(const ScreenArgs s)
 #pragma unroll
             for (int l = 0; l < TILE; l++) {
                 const int lsh = lsh0 + l;
-                if (ksh > ish || lsh > ksh || bas_ij < ksh * nbas + lsh) continue;
+                if (ksh > ish || lsh > ksh || bas_ij < (long long)ksh * nbas + lsh) continue;
                 const float q_ijkl = q_ij + qkl[l];
                 float d_large = -36.8f;
                 if (s.do_k) {
@@ -233,8 +225,8 @@ __global__ void dm_from_mol_kernel(const double* __restrict__ mol, int mol_nao, 
                                    const int* __restrict__ angs, const int* __restrict__ mol_off, XformTab t,
                                    int transpose_out)
 {
-    const int nu = blockIdx.x * blockDim.x + threadIdx.x;
-    const int mu = blockIdx.y;
+    const int nu = blockIdx.y * blockDim.x + threadIdx.x;
+    const int mu = blockIdx.x;
     if (nu >= nao) return;
     const size_t b = blockIdx.z;
     const int s1 = ao2shell[mu], s2 = ao2shell[nu];
@@ -284,8 +276,8 @@ __global__ void dm_to_mol_kernel(const double* __restrict__ kern, int nao, int n
                                  const int* __restrict__ child_ptr, const int* __restrict__ child_list,
                                  const int* __restrict__ ao_loc, const int* __restrict__ angs, XformTab t)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    const int p = blockIdx.y;
+    const int q = blockIdx.y * blockDim.x + threadIdx.x;
+    const int p = blockIdx.x;
     if (q >= mol_nao) return;
     const size_t b = blockIdx.z;
     const int P = molao_parent[p], Q = molao_parent[q];

@@ -1,0 +1,433 @@
+// "Brick" FP64 Rys J/K kernel for the angular classes whose integral block fits one thread's
+// registers (<= JQC_SMALL_N integrals).
+//
+// Replaces, for those classes, the pair screen_jk_tasks -> rys_1q1t_vjk of the reference
+// (jqc/backend/jk/screen_jk_tasks.cu:75-340, jqc/backend/jk/1q1t.cu:45-644; SURVEY rows a9 + a11).
+// The reference (and round 1 of this repository) materialises a list of shell quartets and lets
+// every quartet scatter its six J/K blocks with one FP64 atomic per element: <= 6 nf^2 atomics per
+// quartet, which on B200 sit on the L2's atomic rate (profiles/microbench/atomics.cu).  Here the
+// output is held stationary instead:
+//
+//   * a warp owns a BRICK: 32 (k,l) shell pairs of one group pair (one per lane, neighbours in a
+//     q-descending pair list, so the 32 Schwarz bounds are nearly equal and the lanes pass or fail
+//     the screening together) x a range of bra shells i;
+//   * for each i the warp walks i's partner list j (q-descending, so the loop ends at the first j
+//     whose bound fails) and every lane evaluates (ij|kl) for its own (k,l) in registers;
+//   * J_kl stays in the lane's registers for the whole brick, K_ik and K_il for the whole j loop of
+//     one i; J_ij is the same address for all 32 lanes and is summed with shuffles; only K_jk and
+//     K_jl (nfj (nfk + nfl) elements, the two smallest blocks because lj <= li) are scattered per
+//     quartet.  For (ps|ps) that is 4 atomics per quartet instead of 19;
+//   * the Schwarz x density test of the reference (same float32 arithmetic, same canonical order,
+//     same tile-pair prefilter) runs per lane inside the loop: no quartet list, no second kernel.
+#pragma once
+#include "jk_1q1t.cuh"
+
+namespace jqc {
+
+struct BrickArgs {
+    int nao, nbas;
+    int npi, npj, npk, npl;
+    const double* __restrict__ basis;
+    const double* __restrict__ dm;            // one kernel-side density matrix (nao x nao)
+    double* __restrict__ vj;
+    double* __restrict__ vk;
+    double omega;
+    const float* __restrict__ logd;           // nbas x nbas log density pool (jk.py:179-184)
+    const int* __restrict__ log_max_ordered;
+    float cutoff;                             // log(cutoff): evaluate quartets whose estimate is above
+    // ket side: ordered pair list of the (gk, gl) group pair
+    const ushort2* __restrict__ kl;
+    const float* __restrict__ kl_q;           // q of the pair
+    const float* __restrict__ kl_tq;          // max q of the pair's 4x4 tile (tile-pair prefilter, jk.py:385-431)
+    int n_kl;
+    // bra side: shells i of group gi, each with a q-descending list of partners j in group gj
+    int i_first, i_count;
+    const int* __restrict__ j_off;            // i_count + 1 offsets into the three arrays below
+    const unsigned short* __restrict__ j_idx;
+    const float* __restrict__ j_q;
+    const float* __restrict__ j_tq;
+    float qmax_ij;                            // largest q of the bra group pair
+    int tri;                                  // gi == gk: k <= i and (k,l) <= (i,j) must be tested per lane
+    int ichunk, n_ichunk, n_blk;              // task = (ket block of 32 pairs) x (chunk of bra shells)
+    int rank, world;                          // this GPU takes tasks rank, rank + world, ...
+    unsigned* __restrict__ work;              // dynamic task counter (zeroed per build)
+    unsigned long long* __restrict__ qcount;  // evaluated quartets (accounting)
+};
+
+// One shell quartet, all in registers: eri[N] += contracted integrals (reference: 1q1t.cu:86-405).
+template <int LI, int LJ, int LK, int LL>
+__device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const double* __restrict__ bi,
+                                               const double* __restrict__ bj, const double* __restrict__ bk,
+                                               const double* __restrict__ bl, const double4 ri, const double4 rj,
+                                               const double4 rk, const double4 rl, const int npi, const int npj,
+                                               const int npk, const int npl, const double omega, const double fac)
+{
+    using S = QuartetShape<LI, LJ, LK, LL>;
+    constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
+    constexpr int NROOTS = S::NROOTS, GS = S::GSIZE, DJ = S::DJ, DK = S::DK, DL = S::DL;
+    const double rjri[3] = {rj.x - ri.x, rj.y - ri.y, rj.z - ri.z};
+    const double rlrk[3] = {rl.x - rk.x, rl.y - rk.y, rl.z - rk.z};
+    const double rr_ij = rjri[0] * rjri[0] + rjri[1] * rjri[1] + rjri[2] * rjri[2];
+    const double rr_kl = rlrk[0] * rlrk[0] + rlrk[1] * rlrk[1] + rlrk[2] * rlrk[2];
+#pragma unroll
+    for (int n = 0; n < N; n++) eri[n] = 0.0;
+#pragma unroll 1
+    for (int kp = 0; kp < npk; kp++)
+#pragma unroll 1
+    for (int lp = 0; lp < npl; lp++) {
+        const double2 cek = *reinterpret_cast<const double2*>(bk + 4 + 2 * kp);
+        const double2 cel = *reinterpret_cast<const double2*>(bl + 4 + 2 * lp);
+        const double akl = cek.y + cel.y;
+        const double inv_akl = 1.0 / akl;
+        const double al_akl = cel.y * inv_akl;
+        const double ckcl = cek.x * cel.x * exp(-cek.y * al_akl * rr_kl);
+        const double qx = fma(rlrk[0], al_akl, rk.x), qy = fma(rlrk[1], al_akl, rk.y), qz = fma(rlrk[2], al_akl, rk.z);
+#pragma unroll 1
+        for (int ip = 0; ip < npi; ip++)
+#pragma unroll 1
+        for (int jp = 0; jp < npj; jp++) {
+            const double2 cei = *reinterpret_cast<const double2*>(bi + 4 + 2 * ip);
+            const double2 cej = *reinterpret_cast<const double2*>(bj + 4 + 2 * jp);
+            const double aij = cei.y + cej.y;
+            const double inv_aij = 1.0 / aij;
+            const double aj_aij = cej.y * inv_aij;
+            const double cicj = fac * cei.x * cej.x * exp(-cei.y * aj_aij * rr_ij);
+            const double Rpq[3] = {fma(rjri[0], aj_aij, ri.x) - qx, fma(rjri[1], aj_aij, ri.y) - qy,
+                                   fma(rjri[2], aj_aij, ri.z) - qz};
+            const double rr = Rpq[0] * Rpq[0] + Rpq[1] * Rpq[1] + Rpq[2] * Rpq[2];
+            const double inv_aijkl = 1.0 / (aij + akl);
+            const double theta = aij * akl * inv_aijkl;
+            const double gy0 = cicj * inv_aij * inv_akl * sqrt(inv_aijkl);
+            double rw[2 * NROOTS];
+            double theta_fac = 1.0, sqrt_theta_fac = 1.0;
+            if (omega > 0.0) {
+                const double o2 = omega * omega;
+                theta_fac = o2 / (o2 + theta);
+                sqrt_theta_fac = sqrt(theta_fac);
+            }
+            rys_roots<NROOTS>(rr * theta * theta_fac, rw);
+#pragma unroll 1
+            for (int ir = 0; ir < NROOTS; ir++) {
+                const double rt = rw[2 * ir] * theta_fac;
+                const double wt = rw[2 * ir + 1] * sqrt_theta_fac;
+                const double rt_aa = rt * inv_aijkl;
+                const double rt_aij = rt_aa * akl, rt_akl = rt_aa * aij;
+                const double b10 = 0.5 * inv_aij * (1.0 - rt_aij);
+                const double b01 = 0.5 * inv_akl * (1.0 - rt_akl);
+                const double b00 = 0.5 * rt_aa;
+                double c0[3], cp[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    c0[d] = fma(rjri[d], aj_aij, -rt_aij * Rpq[d]);
+                    cp[d] = fma(rlrk[d], al_akl, rt_akl * Rpq[d]);
+                }
+                double g[3 * GS];
+                fill_g_small<LI, LJ, LK, LL>(g, ckcl, gy0, wt, c0, cp, b10, b01, b00, rjri, rlrk);
+#pragma unroll
+                for (int i = 0; i < NFI; i++)
+#pragma unroll
+                for (int j = 0; j < NFJ; j++)
+#pragma unroll
+                for (int k = 0; k < NFK; k++)
+#pragma unroll
+                for (int l = 0; l < NFL; l++) {
+                    const int ax = CART_X[LI][i] + CART_X[LJ][j] * DJ + CART_X[LK][k] * DK + CART_X[LL][l] * DL;
+                    const int ay = CART_Y[LI][i] + CART_Y[LJ][j] * DJ + CART_Y[LK][k] * DK + CART_Y[LL][l] * DL;
+                    const int az = CART_Z[LI][i] + CART_Z[LJ][j] * DJ + CART_Z[LK][k] * DK + CART_Z[LL][l] * DL;
+                    const int n = ((i * NFJ + j) * NFK + k) * NFL + l;
+                    eri[n] = fma(g[ax] * g[GS + ay], g[2 * GS + az], eri[n]);
+                }
+            }
+        }
+    }
+}
+
+// Per-class choices: where the per-i K accumulators live and how many warps share a CTA.
+template <int LI, int LJ, int LK, int LL>
+struct BrickPlan {
+    using S = QuartetShape<LI, LJ, LK, LL>;
+    static constexpr int NKI = S::NFI * (S::NFK + S::NFL);      // K_ik + K_il accumulators per lane
+    static constexpr int NJKL = S::NFK * S::NFL;                // J_kl accumulators per lane
+    // registers while the integral block + accumulators stay small, lane-private shared memory above
+    static constexpr bool ACC_SMEM = (S::N + NKI + NJKL > 80) && (NKI > 12);
+    static constexpr int NWARPS = 4;
+    static constexpr size_t SMEM = ACC_SMEM ? (size_t)NWARPS * 32 * NKI * sizeof(double) : 0;
+    // register budget per thread -> CTAs of 128 threads per SM: 255 -> 2, 168 -> 3, 128 -> 4
+    static constexpr int REGS = (S::N + NKI + NJKL <= 12) ? 128 : ((S::N + NKI + NJKL <= 36) ? 168 : 255);
+    static constexpr int MINB = 65536 / (REGS * NWARPS * 32);
+    static constexpr bool FITS = SMEM * MINB <= 200 * 1024;
+};
+
+template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K>
+__global__ void __launch_bounds__(BrickPlan<LI, LJ, LK, LL>::NWARPS * 32, BrickPlan<LI, LJ, LK, LL>::MINB)
+jk_brick_kernel(const BrickArgs a)
+{
+    using S = QuartetShape<LI, LJ, LK, LL>;
+    using P = BrickPlan<LI, LJ, LK, LL>;
+    constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ double brick_smem[];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nao = a.nao, nbas = a.nbas;
+    const float log_max = ordered_to_float(*a.log_max_ordered);
+    const float dmaxf = fmaxf(log_max, -36.8f);
+    const double paircut = log(1e-13) - (double)log_max;       // jk.py:185-187, 412
+    const unsigned ntask = (unsigned)a.n_blk * (unsigned)a.n_ichunk;
+    // lane-private accumulator slots [element][lane] (conflict-free)
+    double* __restrict__ sacc = brick_smem + (size_t)warp * 32 * P::NKI + lane;
+    unsigned long long nq = 0;
+
+#pragma unroll 1
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(a.work, 1u);
+        t = __shfl_sync(FULL, t, 0) * (unsigned)a.world + (unsigned)a.rank;
+        if (t >= ntask) break;
+        const int blk = (int)(t % (unsigned)a.n_blk), ic = (int)(t / (unsigned)a.n_blk);
+        const int p = blk * 32 + lane;
+        const bool pvalid = p < a.n_kl;
+        const int pp = pvalid ? p : blk * 32;
+        const ushort2 kl = a.kl[pp];
+        const float q_kl = a.kl_q[pp];
+        const bool lane_on = pvalid && ((double)a.kl_tq[pp] > paircut);
+        float Qb = lane_on ? q_kl : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) Qb = fmaxf(Qb, __shfl_xor_sync(FULL, Qb, o));
+        if (!(a.qmax_ij + Qb + dmaxf > a.cutoff)) continue;
+        const int ksh = kl.x, lsh = kl.y;
+        int kmin = lane_on ? ksh : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(FULL, kmin, o));
+        const double* __restrict__ bk = a.basis + ksh * BASIS_STRIDE;
+        const double* __restrict__ bl = a.basis + lsh * BASIS_STRIDE;
+        const double4 rk = *reinterpret_cast<const double4*>(bk);
+        const double4 rl = *reinterpret_cast<const double4*>(bl);
+        const int k0 = (int)rk.w, l0 = (int)rl.w;
+        const float d_kl = a.logd[(size_t)ksh * nbas + lsh];
+        const double* __restrict__ dm = a.dm;
+
+        double jkl[DO_J ? NFK * NFL : 1];
+        if constexpr (DO_J) {
+#pragma unroll
+            for (int e = 0; e < NFK * NFL; e++) jkl[e] = 0.0;
+        }
+        bool touched_kl = false;
+
+        const int i_lo = a.i_first + ic * a.ichunk;
+        const int i_hi = min(a.i_first + a.i_count, i_lo + a.ichunk);
+#pragma unroll 1
+        for (int ish = i_lo; ish < i_hi; ish++) {
+            if (a.tri && ish < kmin) continue;
+            int e = a.j_off[ish - a.i_first];
+            const int e_end = a.j_off[ish - a.i_first + 1];
+            if (e == e_end) continue;
+            if (!(a.j_q[e] + Qb + dmaxf > a.cutoff)) continue;
+            const double* __restrict__ bi = a.basis + ish * BASIS_STRIDE;
+            const double4 ri = *reinterpret_cast<const double4*>(bi);
+            const int i0 = (int)ri.w;
+            const float d_ik = a.logd[(size_t)ish * nbas + ksh], d_il = a.logd[(size_t)ish * nbas + lsh];
+            const bool lane_i = lane_on && (!a.tri || ksh <= ish);
+
+            double kacc[(DO_K && !P::ACC_SMEM) ? P::NKI : 1];
+            if constexpr (DO_K) {
+                if constexpr (P::ACC_SMEM) {
+#pragma unroll
+                    for (int x = 0; x < P::NKI; x++) sacc[x * 32] = 0.0;
+                } else {
+#pragma unroll
+                    for (int x = 0; x < P::NKI; x++) kacc[x] = 0.0;
+                }
+            }
+            bool touched_i = false;
+
+#pragma unroll 1
+            for (; e < e_end; e++) {
+                const float q_ij = a.j_q[e];
+                if (!(q_ij + Qb + dmaxf > a.cutoff)) break;         // q-descending list: nothing further passes
+                if (!((double)a.j_tq[e] > paircut)) continue;      // bra tile pair not active
+                const int jsh = a.j_idx[e];
+                // canonical order (screen_jk_tasks.cu:202, 225, 239) + Schwarz x density test (:241-261)
+                bool live = lane_i && (!a.tri || ksh < ish || lsh <= jsh);
+                if (live) {
+                    const float q_ijkl = q_ij + q_kl;
+                    float d_large = -36.8f;
+                    if constexpr (DO_K) {
+                        d_large = fmaxf(d_large, d_ik);
+                        d_large = fmaxf(d_large, a.logd[(size_t)jsh * nbas + ksh]);
+                        d_large = fmaxf(d_large, d_il);
+                        d_large = fmaxf(d_large, a.logd[(size_t)jsh * nbas + lsh]);
+                    }
+                    if constexpr (DO_J) {
+                        d_large = fmaxf(d_large, a.logd[(size_t)ish * nbas + jsh]);
+                        d_large = fmaxf(d_large, d_kl);
+                    }
+                    live = q_ijkl + d_large > a.cutoff;
+                }
+                const unsigned m = __ballot_sync(FULL, live);
+                if (m == 0) continue;
+                if (lane == 0) nq += __popc(m);
+                touched_i |= live;
+
+                const double* __restrict__ bj = a.basis + jsh * BASIS_STRIDE;
+                const double4 rj = *reinterpret_cast<const double4*>(bj);
+                const int j0 = (int)rj.w;
+                double fac = live ? PI_FAC : 0.0;
+                if (ish == jsh) fac *= 0.5;
+                if (ksh == lsh) fac *= 0.5;
+                if (ish == ksh && jsh == lsh) fac *= 0.5;
+                double eri[N];
+                eri_block_regs<LI, LJ, LK, LL>(eri, bi, bj, bk, bl, ri, rj, rk, rl, a.npi, a.npj, a.npk, a.npl,
+                                               a.omega, fac);
+#define ERI_(i, j, k, l) eri[(((i) * NFJ + (j)) * NFK + (k)) * NFL + (l)]
+                if constexpr (DO_J) {
+                    // J_kl += sum_ij (ij|kl) D[j,i]: lane-stationary
+                    double d_ji[NFI * NFJ];
+#pragma unroll
+                    for (int i = 0; i < NFI; i++)
+#pragma unroll
+                    for (int j = 0; j < NFJ; j++) d_ji[i * NFJ + j] = __ldg(dm + (size_t)(j0 + j) * nao + i0 + i);
+#pragma unroll
+                    for (int k = 0; k < NFK; k++)
+#pragma unroll
+                    for (int l = 0; l < NFL; l++) {
+                        double s = jkl[k * NFL + l];
+#pragma unroll
+                        for (int i = 0; i < NFI; i++)
+#pragma unroll
+                        for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji[i * NFJ + j], s);
+                        jkl[k * NFL + l] = s;
+                    }
+                    // J_ij += sum_kl (ij|kl) D[l,k]: one address for the whole warp -> shuffle sum
+                    double d_lk[NFK * NFL];
+#pragma unroll
+                    for (int k = 0; k < NFK; k++)
+#pragma unroll
+                    for (int l = 0; l < NFL; l++) d_lk[k * NFL + l] = __ldg(dm + (size_t)(l0 + l) * nao + k0 + k);
+#pragma unroll
+                    for (int i = 0; i < NFI; i++)
+#pragma unroll
+                    for (int j = 0; j < NFJ; j++) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NFK; k++)
+#pragma unroll
+                        for (int l = 0; l < NFL; l++) s = fma(ERI_(i, j, k, l), d_lk[k * NFL + l], s);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+                        if (lane == ((i * NFJ + j) & 31)) atomicAdd(a.vj + (size_t)(j0 + j) * nao + i0 + i, s);
+                    }
+                }
+                if constexpr (DO_K) {
+                    {   // K_ik += sum_jl (ij|kl) D[j,l]: stationary over the j loop
+                        double d[NFJ * NFL];
+#pragma unroll
+                        for (int j = 0; j < NFJ; j++)
+#pragma unroll
+                        for (int l = 0; l < NFL; l++) d[j * NFL + l] = __ldg(dm + (size_t)(j0 + j) * nao + l0 + l);
+#pragma unroll
+                        for (int i = 0; i < NFI; i++)
+#pragma unroll
+                        for (int k = 0; k < NFK; k++) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int j = 0; j < NFJ; j++)
+#pragma unroll
+                            for (int l = 0; l < NFL; l++) s = fma(ERI_(i, j, k, l), d[j * NFL + l], s);
+                            if constexpr (P::ACC_SMEM) sacc[(i * NFK + k) * 32] += s;
+                            else kacc[i * NFK + k] += s;
+                        }
+                    }
+                    {   // K_il += sum_jk (ij|kl) D[j,k]: stationary over the j loop
+                        double d[NFJ * NFK];
+#pragma unroll
+                        for (int j = 0; j < NFJ; j++)
+#pragma unroll
+                        for (int k = 0; k < NFK; k++) d[j * NFK + k] = __ldg(dm + (size_t)(j0 + j) * nao + k0 + k);
+#pragma unroll
+                        for (int i = 0; i < NFI; i++)
+#pragma unroll
+                        for (int l = 0; l < NFL; l++) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int j = 0; j < NFJ; j++)
+#pragma unroll
+                            for (int k = 0; k < NFK; k++) s = fma(ERI_(i, j, k, l), d[j * NFK + k], s);
+                            if constexpr (P::ACC_SMEM) sacc[(NFI * NFK + i * NFL + l) * 32] += s;
+                            else kacc[NFI * NFK + i * NFL + l] += s;
+                        }
+                    }
+                    {   // K_jk += sum_il (ij|kl) D[i,l]: scattered per quartet
+                        double d[NFI * NFL];
+#pragma unroll
+                        for (int i = 0; i < NFI; i++)
+#pragma unroll
+                        for (int l = 0; l < NFL; l++) d[i * NFL + l] = __ldg(dm + (size_t)(i0 + i) * nao + l0 + l);
+#pragma unroll
+                        for (int j = 0; j < NFJ; j++)
+#pragma unroll
+                        for (int k = 0; k < NFK; k++) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int i = 0; i < NFI; i++)
+#pragma unroll
+                            for (int l = 0; l < NFL; l++) s = fma(ERI_(i, j, k, l), d[i * NFL + l], s);
+                            if (live) atomicAdd(a.vk + (size_t)(j0 + j) * nao + k0 + k, s);
+                        }
+                    }
+                    {   // K_jl += sum_ik (ij|kl) D[i,k]: scattered per quartet
+                        double d[NFI * NFK];
+#pragma unroll
+                        for (int i = 0; i < NFI; i++)
+#pragma unroll
+                        for (int k = 0; k < NFK; k++) d[i * NFK + k] = __ldg(dm + (size_t)(i0 + i) * nao + k0 + k);
+#pragma unroll
+                        for (int j = 0; j < NFJ; j++)
+#pragma unroll
+                        for (int l = 0; l < NFL; l++) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int i = 0; i < NFI; i++)
+#pragma unroll
+                            for (int k = 0; k < NFK; k++) s = fma(ERI_(i, j, k, l), d[i * NFK + k], s);
+                            if (live) atomicAdd(a.vk + (size_t)(j0 + j) * nao + l0 + l, s);
+                        }
+                    }
+                }
+#undef ERI_
+            }
+            // flush the per-i K accumulators of the lanes that contributed
+            if constexpr (DO_K) {
+                if (touched_i) {
+#pragma unroll
+                    for (int i = 0; i < NFI; i++)
+#pragma unroll
+                    for (int k = 0; k < NFK; k++) {
+                        const double v = P::ACC_SMEM ? sacc[(i * NFK + k) * 32] : kacc[(P::ACC_SMEM ? 0 : i * NFK + k)];
+                        atomicAdd(a.vk + (size_t)(i0 + i) * nao + k0 + k, v);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NFI; i++)
+#pragma unroll
+                    for (int l = 0; l < NFL; l++) {
+                        const double v = P::ACC_SMEM ? sacc[(NFI * NFK + i * NFL + l) * 32]
+                                                     : kacc[(P::ACC_SMEM ? 0 : NFI * NFK + i * NFL + l)];
+                        atomicAdd(a.vk + (size_t)(i0 + i) * nao + l0 + l, v);
+                    }
+                }
+            }
+            touched_kl |= touched_i;
+        }
+        if constexpr (DO_J) {
+            if (touched_kl) {
+#pragma unroll
+                for (int k = 0; k < NFK; k++)
+#pragma unroll
+                for (int l = 0; l < NFL; l++) atomicAdd(a.vj + (size_t)(l0 + l) * nao + k0 + k, jkl[k * NFL + l]);
+            }
+        }
+    }
+    if (lane == 0 && nq) atomicAdd(a.qcount, nq);
+}
+
+}  // namespace jqc

@@ -2,11 +2,40 @@
 // Instantiates the J/K kernels for every ket class lk <= li, ll <= lk and the three
 // (do_j, do_k) variants, and exports one launcher.  (The reference JIT-compiles the same
 // specialisations at run time through NVRTC: jqc/backend/jk.py:56-115.)
+#include <atomic>
+
 #include "jk_tile16.cuh"
 #include "jk_warp.cuh"
+#include "jk_brick.cuh"
 #include "jk_launch.h"
 
 namespace jqc {
+
+// Occupancy and the dynamic shared-memory opt-in are per device (function attributes do not
+// carry over to another GPU of the same process): cached per device ordinal.  A racing first
+// call repeats idempotent work.
+constexpr int JQC_MAX_DEVICES = 64;
+template <class K>
+static cudaError_t blocks_per_sm_cached(std::atomic<int>* cache, K kern, int threads, size_t smem, int* out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= JQC_MAX_DEVICES) return cudaErrorInvalidDevice;
+    int nb = cache[dev].load(std::memory_order_acquire);
+    if (nb == 0) {
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem);
+        if (e != cudaSuccess) return e;
+        nb = nb > 0 ? nb : 1;
+        cache[dev].store(nb, std::memory_order_release);
+    }
+    *out = nb;
+    return cudaSuccess;
+}
 
 // Multi-lane kernel: warps per block chosen so that two blocks fit the 227 KB of an SM when possible.
 template <int LK, int LL>
@@ -30,17 +59,35 @@ static cudaError_t launch_warp(const JKArgs& a, int nsm, cudaStream_t st)
 {
     using C = WarpCfg<LK, LL>;
     auto kern = jk_warp_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, C::NWARPS>;
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return e;
-        int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::NWARPS * 32, C::SMEM);
-        if (e != cudaSuccess) return e;
-        blocks_per_sm = nb > 0 ? nb : 1;
-    }
+    static std::atomic<int> cache[JQC_MAX_DEVICES];
+    int blocks_per_sm = 1;
+    cudaError_t e = blocks_per_sm_cached(cache, kern, C::NWARPS * 32, C::SMEM, &blocks_per_sm);
+    if (e != cudaSuccess) return e;
     kern<<<nsm * blocks_per_sm, C::NWARPS * 32, C::SMEM, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int LK, int LL, bool DO_J, bool DO_K>
+static cudaError_t launch_brick(const BrickArgs& a, int nsm, cudaStream_t st)
+{
+    using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
+    using P = BrickPlan<JQC_LI, JQC_LJ, LK, LL>;
+    if constexpr (S::N <= JQC_SMALL_N && P::FITS) {
+        auto kern = jk_brick_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K>;
+        static std::atomic<int> cache[JQC_MAX_DEVICES];
+        int blocks_per_sm = 1;
+        cudaError_t e = blocks_per_sm_cached(cache, kern, P::NWARPS * 32, P::SMEM, &blocks_per_sm);
+        if (e != cudaSuccess) return e;
+        // no more warps than tasks
+        const long long ntask = ((long long)a.n_blk * a.n_ichunk + a.world - 1) / a.world;
+        long long blocks = (ntask + P::NWARPS - 1) / P::NWARPS;
+        if (blocks > (long long)nsm * blocks_per_sm) blocks = (long long)nsm * blocks_per_sm;
+        if (blocks < 1) blocks = 1;
+        kern<<<(unsigned)blocks, P::NWARPS * 32, P::SMEM, st>>>(a);
+        return cudaGetLastError();
+    } else {
+        return cudaErrorInvalidValue;
+    }
 }
 
 template <int LK, int LL, bool DO_J, bool DO_K, bool TILES>
@@ -49,23 +96,22 @@ static cudaError_t launch_one(const JKArgs& a, int nsm, cudaStream_t st)
     using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
     if constexpr (S::N > JQC_SMALL_N && WarpCfg<LK, LL>::FITS && JQC_LI <= 3) {
         return launch_warp<LK, LL, DO_J, DO_K>(a, nsm, st);
-    }
-    constexpr bool SMALL = S::N <= JQC_SMALL_N;
-    constexpr int NT = SMALL ? 256 : 128;
-    static_assert(JQC_TILE16_N == 81, "keep jk_uses_tiles() in jk_launch.h in sync");
-    void (*kern)(const JKArgs);
-    if constexpr (SMALL) kern = TILES ? jk_tile16_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>
-                                      : jk_1q1t_kernel_small<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
-    else kern = jk_1q1t_kernel_large<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        int nb = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, 0);
+    } else {
+        // (else-branch so that the rolled fallback is only instantiated for the classes that use it)
+        constexpr bool SMALL = S::N <= JQC_SMALL_N;
+        constexpr int NT = SMALL ? 256 : 128;
+        static_assert(JQC_TILE16_N == 81, "keep jk_uses_tiles() in jk_launch.h in sync");
+        void (*kern)(const JKArgs);
+        if constexpr (SMALL) kern = TILES ? jk_tile16_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>
+                                          : jk_1q1t_kernel_small<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
+        else kern = jk_1q1t_kernel_large<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, NT>;
+        static std::atomic<int> cache[JQC_MAX_DEVICES];
+        int blocks_per_sm = 1;
+        cudaError_t e = blocks_per_sm_cached(cache, kern, NT, 0, &blocks_per_sm);
         if (e != cudaSuccess) return e;
-        blocks_per_sm = nb > 0 ? nb : 1;
+        kern<<<nsm * blocks_per_sm, NT, 0, st>>>(a);
+        return cudaGetLastError();
     }
-    kern<<<nsm * blocks_per_sm, NT, 0, st>>>(a);
-    return cudaGetLastError();
 }
 
 template <int LK, int LL>
@@ -107,6 +153,38 @@ static cudaError_t dispatch(int lk, int ll, int variant, const JKArgs& a, int ns
 cudaError_t JQC_CAT(jk_launch_, JQC_LI, JQC_LJ)(int lk, int ll, int variant, const JKArgs& a, int nsm, cudaStream_t st)
 {
     return dispatch<0>(lk, ll, variant, a, nsm, st);
+}
+
+template <int LK, int LL>
+static cudaError_t brick_variant(int variant, const BrickArgs& a, int nsm, cudaStream_t st)
+{
+    switch (variant) {
+        case 3: return launch_brick<LK, LL, true, true>(a, nsm, st);
+        case 1: return launch_brick<LK, LL, true, false>(a, nsm, st);
+        case 2: return launch_brick<LK, LL, false, true>(a, nsm, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int Z>
+static cudaError_t brick_dispatch(int lk, int ll, int variant, const BrickArgs& a, int nsm, cudaStream_t st)
+{
+#define CASE(K, L)                                                       \
+    if constexpr (K + Z <= JQC_LI && L <= K) {                           \
+        if (lk == K && ll == L) return brick_variant<K, L>(variant, a, nsm, st); \
+    }
+    CASE(0, 0)
+    CASE(1, 0) CASE(1, 1)
+    CASE(2, 0) CASE(2, 1) CASE(2, 2)
+    CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)
+    CASE(4, 0) CASE(4, 1) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+#undef CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t JQC_CAT(jk_brick_launch_, JQC_LI, JQC_LJ)(int lk, int ll, int variant, const BrickArgs& a, int nsm, cudaStream_t st)
+{
+    return brick_dispatch<0>(lk, ll, variant, a, nsm, st);
 }
 
 }  // namespace jqc

@@ -4,7 +4,10 @@
 
 namespace jqc {
 struct JKArgs;
-#define JQC_DECL(I, J) cudaError_t jk_launch_##I##_##J(int lk, int ll, int variant, const JKArgs& a, int nsm, cudaStream_t st);
+struct BrickArgs;
+#define JQC_DECL(I, J)                                                                                          \
+    cudaError_t jk_launch_##I##_##J(int lk, int ll, int variant, const JKArgs& a, int nsm, cudaStream_t st);    \
+    cudaError_t jk_brick_launch_##I##_##J(int lk, int ll, int variant, const BrickArgs& a, int nsm, cudaStream_t st);
 JQC_DECL(0, 0)
 JQC_DECL(1, 0) JQC_DECL(1, 1)
 JQC_DECL(2, 0) JQC_DECL(2, 1) JQC_DECL(2, 2)
@@ -26,6 +29,30 @@ inline bool jk_uses_tiles(int li, int lj, int lk, int ll)
 inline cudaError_t jk_launch(int li, int lj, int lk, int ll, int variant, const JKArgs& a, int nsm, cudaStream_t st)
 {
 #define JQC_CALL(I, J) if (li == I && lj == J) return jk_launch_##I##_##J(lk, ll, variant, a, nsm, st);
+    JQC_CALL(0, 0)
+    JQC_CALL(1, 0) JQC_CALL(1, 1)
+    JQC_CALL(2, 0) JQC_CALL(2, 1) JQC_CALL(2, 2)
+    JQC_CALL(3, 0) JQC_CALL(3, 1) JQC_CALL(3, 2) JQC_CALL(3, 3)
+    JQC_CALL(4, 0) JQC_CALL(4, 1) JQC_CALL(4, 2) JQC_CALL(4, 3) JQC_CALL(4, 4)
+#undef JQC_CALL
+    return cudaErrorInvalidValue;
+}
+
+// Classes that run on the brick kernel (jk_brick.cuh): integral block in one thread's registers and
+// the per-i K accumulators within the shared-memory budget.  Mirrors BrickPlan<>.
+inline bool jk_brick_supported(int li, int lj, int lk, int ll)
+{
+    auto nf = [](int l) { return (l + 1) * (l + 2) / 2; };
+    const int n = nf(li) * nf(lj) * nf(lk) * nf(ll);
+    if (n > JQC_SMALL_N_VALUE) return false;
+    const int nki = nf(li) * (nf(lk) + nf(ll)), njkl = nf(lk) * nf(ll);
+    const bool acc_smem = (n + nki + njkl > 80) && nki > 12;
+    return !acc_smem || (size_t)2 * 4 * 32 * nki * sizeof(double) <= 200 * 1024;   // 2 CTAs of 4 warps at 255 registers
+}
+
+inline cudaError_t jk_brick_launch(int li, int lj, int lk, int ll, int variant, const BrickArgs& a, int nsm, cudaStream_t st)
+{
+#define JQC_CALL(I, J) if (li == I && lj == J) return jk_brick_launch_##I##_##J(lk, ll, variant, a, nsm, st);
     JQC_CALL(0, 0)
     JQC_CALL(1, 0) JQC_CALL(1, 1)
     JQC_CALL(2, 0) JQC_CALL(2, 1) JQC_CALL(2, 2)

@@ -59,6 +59,14 @@ __device__ constexpr signed char CART_Z[5][15] = {
     {0,0,1,0,1,2,0,1,2,3,0,0,0,0,0},
     {0,0,1,0,1,2,0,1,2,3,0,1,2,3,4}};
 
+// ------------------------------------------------------------------ ordered float <-> int
+__device__ __forceinline__ int float_to_ordered(float f)
+{
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
 // Packed record: [x, y, z, ao_loc, c0, e0, c1, e1, c2, e2, 0, 0]
 struct ShellHead {
     double x, y, z, ao;

@@ -258,3 +258,68 @@ def test_python_partial_finalize_api(torch_cuda):
     assert buf.numel() == 2 * lay.nao * lay.nao
     vj, vk = eng.finalize()
     assert (vj - ref_j).abs().max().item() < 1e-11 and (vk - ref_k).abs().max().item() < 1e-11
+
+
+# ---------------------------------------------------------------------------------------
+# Engine paths selected by environment knobs (read at engine creation): every parity case
+# below builds a fresh layout -> fresh engine.
+
+def _fresh_check(monkeypatch, env, atom, basis, seed=9, scale=1.0, **kw):
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    mol, lay = make(atom, basis)
+    _check(lay, random_dm(mol.nao, seed) * scale, hermi=1, **kw)
+    return lay
+
+
+def test_quartet_list_path_small_classes(torch_cuda, monkeypatch):
+    """JQC_BRICK=0: the one-quartet-per-thread kernels fed by screen_tasks_kernel (round-1 path,
+    still used for n_dm > 1) against the oracle."""
+    _fresh_check(monkeypatch, {"JQC_BRICK": 0}, H2O, "def2-tzvpp")
+    _fresh_check(monkeypatch, {"JQC_BRICK": 0}, benzene(), "def2-svp", scale=0.05)
+
+
+def test_tile16_path(torch_cuda, monkeypatch):
+    """JQC_SMALL_TILES=1: the 4x4-tile variant of the small-class kernel (jk_tile16.cuh)."""
+    _fresh_check(monkeypatch, {"JQC_SMALL_TILES": 1}, H2O, "def2-tzvpp")
+    _fresh_check(monkeypatch, {"JQC_SMALL_TILES": 1}, benzene(), "def2-svp", scale=0.05)
+
+
+@pytest.mark.parametrize("brick", [0, 1])
+def test_multi_chunk_task_queues(torch_cuda, monkeypatch, brick):
+    """Shrunk queue capacity / kl chunk: benzene/cc-pVTZ then runs with many (ij, kl) chunks per
+    group quartet, i.e. the ij0 > 0 / kl0 > 0 iterations of the engine's chunk loops that only a
+    valinomycin-sized molecule reaches with the production sizes."""
+    monkeypatch.setenv("JQC_BRICK", str(brick))
+    mol, lay0 = make(benzene(), "cc-pvtz")
+    dm = random_dm(mol.nao, 9) / 264
+    lay0.engine().get_jk(dm, hermi=1)
+    _, _, launches0 = lay0.engine().last_stats()
+    lay = _fresh_check(monkeypatch, {"JQC_QUEUE_CAP": 4096, "JQC_KL_CHUNK": 5}, benzene(), "cc-pvtz", scale=1.0 / 264)
+    _, _, launches = lay.engine().last_stats()
+    assert launches > 3 * launches0, (launches, launches0)     # many more chunks were really launched
+
+
+@pytest.mark.parametrize("ichunk", [1, 3, 64])
+def test_brick_chunking(torch_cuda, monkeypatch, ichunk):
+    """brick kernel with different bra-chunk sizes (task decomposition must not change the result)"""
+    lay = _fresh_check(monkeypatch, {"JQC_BRICK_ICHUNK": ichunk}, benzene(), "def2-tzvp", scale=0.02)
+    counts, _, _ = lay.engine().last_stats()
+    orc = _oracle(lay)
+    orc.get_jk(random_dm(lay._mol.nao, 9) * 0.02, 1)
+    assert np.array_equal(counts, orc.last_counts)
+
+
+def test_brick_density_screening_counts(torch_cuda):
+    """brick path, density-dominated screening: same quartets per class as the oracle, J-only and
+    K-only variants use their own density criterion (screen_jk_tasks.cu:241-261)"""
+    mol, lay = make(benzene(), "def2-tzvp")
+    rng = np.random.RandomState(5)
+    dm = rng.randn(mol.nao, mol.nao) * np.exp(-rng.uniform(0, 14, (mol.nao, mol.nao)))
+    dm = dm + dm.T
+    for with_j, with_k in [(True, True), (True, False), (False, True)]:
+        _check(lay, dm, hermi=1, with_j=with_j, with_k=with_k, cutoff=1e-9, tol=1e-12)
+        counts, _, _ = lay.engine().last_stats()
+        orc = _oracle(lay)
+        orc.get_jk(dm, 1, with_j, with_k, None, 1e-9)
+        assert np.array_equal(counts, orc.last_counts), (with_j, with_k)
