@@ -514,7 +514,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
         const int li = e->gl[gi], lj = e->gl[gj], lk = e->gl[gk], ll = e->gl[gl];
         const int key = ((li * 5 + lj) * 5 + lk) * 5 + ll;
         const long long pw = (long long)e->gnp[gi] * e->gnp[gj] * e->gnp[gk] * e->gnp[gl];
-        if (e->use_brick && neff == 1 && !e->small_tiles && jk_brick_supported(li, lj, lk, ll)) {
+        if (e->use_brick && neff == 1 && !e->small_tiles && brick_shape(li, lj, lk, ll).fits) {
             const int n_kl_pairs = qd->h_pair_off[pkl + 1] - qd->h_pair_off[pkl];
             const int n_ij_pairs = qd->h_pair_off[pij + 1] - qd->h_pair_off[pij];
             if (n_kl_pairs == 0 || n_ij_pairs == 0) continue;

@@ -60,7 +60,8 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
                                                const double* __restrict__ bj, const double* __restrict__ bk,
                                                const double* __restrict__ bl, const double4 ri, const double4 rj,
                                                const double4 rk, const double4 rl, const int npi, const int npj,
-                                               const int npk, const int npl, const double omega, const double fac)
+                                               const int npk, const int npl, const double omega, const double fac,
+                                               const double2* __restrict__ s_rys)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
                 theta_fac = o2 / (o2 + theta);
                 sqrt_theta_fac = sqrt(theta_fac);
             }
-            rys_roots<NROOTS>(rr * theta * theta_fac, rw);
+            rys_roots_smem<NROOTS>(rr * theta * theta_fac, rw, s_rys);
 #pragma unroll 1
             for (int ir = 0; ir < NROOTS; ir++) {
                 const double rt = rw[2 * ir] * theta_fac;
@@ -142,20 +143,51 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
     }
 }
 
-// Per-class choices: where the per-i K accumulators live and how many warps share a CTA.
+// Per-class layout of the brick kernel, usable at compile time (BrickPlan) and by the host (which
+// classes are supported, how much dynamic shared memory a launch needs).
+struct BrickShape {
+    int n, nki, njkl, nroots;
+    bool acc_smem;      // per-i K accumulators in lane-private shared memory (else registers)
+    bool di_smem;       // D_il / D_ik blocks (stationary over the j loop) staged in lane-private shared memory
+    int dlk_mode;       // D_lk block (stationary over the brick): 0 registers, 1 lane-private shared memory, 2 reloaded
+    int slots;          // lane-private doubles per lane
+    int regs, minb, nwarps;
+    size_t rys_bytes, smem;
+    bool fits;
+};
+
+__host__ __device__ constexpr BrickShape brick_shape(int li, int lj, int lk, int ll)
+{
+    BrickShape b{};
+    const int nfi = nf_of(li), nfj = nf_of(lj), nfk = nf_of(lk), nfl = nf_of(ll);
+    b.n = nfi * nfj * nfk * nfl;
+    b.nki = nfi * (nfk + nfl);
+    b.njkl = nfk * nfl;
+    b.nroots = (li + lj + lk + ll) / 2 + 1;
+    b.nwarps = 4;
+    const int live = b.n + b.nki + b.njkl;
+    b.acc_smem = live > 80 && b.nki > 12;
+    b.di_smem = b.nki <= 48;
+    b.dlk_mode = b.njkl <= 3 ? 0 : (b.njkl <= 9 ? 1 : 2);
+    b.slots = (b.acc_smem ? b.nki : 0) + (b.di_smem ? b.nki : 0) + (b.dlk_mode == 1 ? b.njkl : 0);
+    // register budget per thread -> CTAs of 128 threads per SM: 255 -> 2, 168 -> 3, 128 -> 4
+    b.regs = live <= 12 ? 128 : (live <= 36 ? 168 : 255);
+    b.minb = 65536 / (b.regs * b.nwarps * 32);
+    b.rys_bytes = (size_t)b.nroots * (14 + 2 * b.nroots) * (RYS_NCOEF + 1) * 16;
+    b.smem = b.rys_bytes + (size_t)b.nwarps * 32 * b.slots * sizeof(double);
+    b.fits = b.n <= JQC_SMALL_N && b.smem * b.minb <= 216 * 1024;
+    return b;
+}
+
 template <int LI, int LJ, int LK, int LL>
 struct BrickPlan {
-    using S = QuartetShape<LI, LJ, LK, LL>;
-    static constexpr int NKI = S::NFI * (S::NFK + S::NFL);      // K_ik + K_il accumulators per lane
-    static constexpr int NJKL = S::NFK * S::NFL;                // J_kl accumulators per lane
-    // registers while the integral block + accumulators stay small, lane-private shared memory above
-    static constexpr bool ACC_SMEM = (S::N + NKI + NJKL > 80) && (NKI > 12);
-    static constexpr int NWARPS = 4;
-    static constexpr size_t SMEM = ACC_SMEM ? (size_t)NWARPS * 32 * NKI * sizeof(double) : 0;
-    // register budget per thread -> CTAs of 128 threads per SM: 255 -> 2, 168 -> 3, 128 -> 4
-    static constexpr int REGS = (S::N + NKI + NJKL <= 12) ? 128 : ((S::N + NKI + NJKL <= 36) ? 168 : 255);
-    static constexpr int MINB = 65536 / (REGS * NWARPS * 32);
-    static constexpr bool FITS = SMEM * MINB <= 200 * 1024;
+    static constexpr BrickShape B = brick_shape(LI, LJ, LK, LL);
+    static constexpr int NKI = B.nki, NJKL = B.njkl, NWARPS = B.nwarps, MINB = B.minb, SLOTS = B.slots;
+    static constexpr bool ACC_SMEM = B.acc_smem, DI_SMEM = B.di_smem, FITS = B.fits;
+    static constexpr int DLK_MODE = B.dlk_mode;
+    static constexpr size_t SMEM = B.smem, RYS_BYTES = B.rys_bytes;
+    // slot offsets (lane-private doubles)
+    static constexpr int S_ACC = 0, S_DI = ACC_SMEM ? NKI : 0, S_DLK = S_DI + (DI_SMEM ? NKI : 0);
 };
 
 template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K>
@@ -166,7 +198,7 @@ jk_brick_kernel(const BrickArgs a)
     using P = BrickPlan<LI, LJ, LK, LL>;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ double brick_smem[];
+    extern __shared__ double2 brick_smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nao = a.nao, nbas = a.nbas;
@@ -174,8 +206,12 @@ jk_brick_kernel(const BrickArgs a)
     const float dmaxf = fmaxf(log_max, -36.8f);
     const double paircut = log(1e-13) - (double)log_max;       // jk.py:185-187, 412
     const unsigned ntask = (unsigned)a.n_blk * (unsigned)a.n_ichunk;
-    // lane-private accumulator slots [element][lane] (conflict-free)
-    double* __restrict__ sacc = brick_smem + (size_t)warp * 32 * P::NKI + lane;
+    // shared memory: [Rys table of this class][lane-private slots: element-major, lane-minor]
+    const double2* __restrict__ s_rys = brick_smem;
+    rys_table_to_smem<S::NROOTS>(brick_smem);
+    double* __restrict__ slot = reinterpret_cast<double*>(brick_smem) + P::RYS_BYTES / sizeof(double) +
+                                (size_t)warp * 32 * P::SLOTS + lane;
+#define SLOT_(x) slot[(x) * 32]
     unsigned long long nq = 0;
 
 #pragma unroll 1
@@ -208,9 +244,16 @@ jk_brick_kernel(const BrickArgs a)
         const double* __restrict__ dm = a.dm;
 
         double jkl[DO_J ? NFK * NFL : 1];
+        double dlk_r[(DO_J && P::DLK_MODE == 0) ? NFK * NFL : 1];
         if constexpr (DO_J) {
 #pragma unroll
-            for (int e = 0; e < NFK * NFL; e++) jkl[e] = 0.0;
+            for (int k = 0; k < NFK; k++)
+#pragma unroll
+            for (int l = 0; l < NFL; l++) {
+                jkl[k * NFL + l] = 0.0;
+                if constexpr (P::DLK_MODE == 0) dlk_r[k * NFL + l] = __ldg(dm + (size_t)(l0 + l) * nao + k0 + k);
+                if constexpr (P::DLK_MODE == 1) SLOT_(P::S_DLK + k * NFL + l) = __ldg(dm + (size_t)(l0 + l) * nao + k0 + k);
+            }
         }
         bool touched_kl = false;
 
@@ -231,12 +274,21 @@ jk_brick_kernel(const BrickArgs a)
 
             double kacc[(DO_K && !P::ACC_SMEM) ? P::NKI : 1];
             if constexpr (DO_K) {
-                if constexpr (P::ACC_SMEM) {
+                // K_ik accumulators at [i * NFK + k], K_il at [NFI * NFK + i * NFL + l]; the D_ik / D_il
+                // blocks use the same indexing in their own slot range
 #pragma unroll
-                    for (int x = 0; x < P::NKI; x++) sacc[x * 32] = 0.0;
-                } else {
+                for (int x = 0; x < P::NKI; x++) {
+                    if constexpr (P::ACC_SMEM) SLOT_(P::S_ACC + x) = 0.0;
+                    else kacc[x] = 0.0;
+                }
+                if constexpr (P::DI_SMEM) {
 #pragma unroll
-                    for (int x = 0; x < P::NKI; x++) kacc[x] = 0.0;
+                    for (int i = 0; i < NFI; i++) {
+#pragma unroll
+                        for (int k = 0; k < NFK; k++) SLOT_(P::S_DI + i * NFK + k) = __ldg(dm + (size_t)(i0 + i) * nao + k0 + k);
+#pragma unroll
+                        for (int l = 0; l < NFL; l++) SLOT_(P::S_DI + NFI * NFK + i * NFL + l) = __ldg(dm + (size_t)(i0 + i) * nao + l0 + l);
+                    }
                 }
             }
             bool touched_i = false;
@@ -278,7 +330,7 @@ jk_brick_kernel(const BrickArgs a)
                 if (ish == ksh && jsh == lsh) fac *= 0.5;
                 double eri[N];
                 eri_block_regs<LI, LJ, LK, LL>(eri, bi, bj, bk, bl, ri, rj, rk, rl, a.npi, a.npj, a.npk, a.npl,
-                                               a.omega, fac);
+                                               a.omega, fac, s_rys);
 #define ERI_(i, j, k, l) eri[(((i) * NFJ + (j)) * NFK + (k)) * NFL + (l)]
                 if constexpr (DO_J) {
                     // J_kl += sum_ij (ij|kl) D[j,i]: lane-stationary
@@ -298,25 +350,30 @@ jk_brick_kernel(const BrickArgs a)
                         for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji[i * NFJ + j], s);
                         jkl[k * NFL + l] = s;
                     }
-                    // J_ij += sum_kl (ij|kl) D[l,k]: one address for the whole warp -> shuffle sum
-                    double d_lk[NFK * NFL];
+                    // J_ij += sum_kl (ij|kl) D[l,k]: one address for the whole warp -> reduce-scatter
+                    double vij[NFI * NFJ];
+#pragma unroll
+                    for (int x = 0; x < NFI * NFJ; x++) vij[x] = 0.0;
 #pragma unroll
                     for (int k = 0; k < NFK; k++)
 #pragma unroll
-                    for (int l = 0; l < NFL; l++) d_lk[k * NFL + l] = __ldg(dm + (size_t)(l0 + l) * nao + k0 + k);
+                    for (int l = 0; l < NFL; l++) {
+                        const double d = P::DLK_MODE == 0 ? dlk_r[P::DLK_MODE == 0 ? k * NFL + l : 0]
+                                       : (P::DLK_MODE == 1 ? SLOT_(P::S_DLK + k * NFL + l)
+                                                           : __ldg(dm + (size_t)(l0 + l) * nao + k0 + k));
 #pragma unroll
-                    for (int i = 0; i < NFI; i++)
+                        for (int i = 0; i < NFI; i++)
 #pragma unroll
-                    for (int j = 0; j < NFJ; j++) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int k = 0; k < NFK; k++)
-#pragma unroll
-                        for (int l = 0; l < NFL; l++) s = fma(ERI_(i, j, k, l), d_lk[k * NFL + l], s);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-                        if (lane == ((i * NFJ + j) & 31)) atomicAdd(a.vj + (size_t)(j0 + j) * nao + i0 + i, s);
+                        for (int j = 0; j < NFJ; j++) vij[i * NFJ + j] = fma(ERI_(i, j, k, l), d, vij[i * NFJ + j]);
                     }
+                    int idx = 0, cnt = NFI * NFJ;
+                    WarpReduceScatter<NFI * NFJ, 16>::run(vij, lane, idx, cnt);
+#pragma unroll
+                    for (int x = 0; x < warp_rs_final(NFI * NFJ); x++)
+                        if (x < cnt) {
+                            const int i = (idx + x) / NFJ, j = (idx + x) - i * NFJ;
+                            atomicAdd(a.vj + (size_t)(j0 + j) * nao + i0 + i, vij[x]);
+                        }
                 }
                 if constexpr (DO_K) {
                     {   // K_ik += sum_jl (ij|kl) D[j,l]: stationary over the j loop
@@ -334,7 +391,7 @@ jk_brick_kernel(const BrickArgs a)
                             for (int j = 0; j < NFJ; j++)
 #pragma unroll
                             for (int l = 0; l < NFL; l++) s = fma(ERI_(i, j, k, l), d[j * NFL + l], s);
-                            if constexpr (P::ACC_SMEM) sacc[(i * NFK + k) * 32] += s;
+                            if constexpr (P::ACC_SMEM) SLOT_(P::S_ACC + i * NFK + k) += s;
                             else kacc[i * NFK + k] += s;
                         }
                     }
@@ -353,16 +410,11 @@ jk_brick_kernel(const BrickArgs a)
                             for (int j = 0; j < NFJ; j++)
 #pragma unroll
                             for (int k = 0; k < NFK; k++) s = fma(ERI_(i, j, k, l), d[j * NFK + k], s);
-                            if constexpr (P::ACC_SMEM) sacc[(NFI * NFK + i * NFL + l) * 32] += s;
+                            if constexpr (P::ACC_SMEM) SLOT_(P::S_ACC + NFI * NFK + i * NFL + l) += s;
                             else kacc[NFI * NFK + i * NFL + l] += s;
                         }
                     }
                     {   // K_jk += sum_il (ij|kl) D[i,l]: scattered per quartet
-                        double d[NFI * NFL];
-#pragma unroll
-                        for (int i = 0; i < NFI; i++)
-#pragma unroll
-                        for (int l = 0; l < NFL; l++) d[i * NFL + l] = __ldg(dm + (size_t)(i0 + i) * nao + l0 + l);
 #pragma unroll
                         for (int j = 0; j < NFJ; j++)
 #pragma unroll
@@ -371,16 +423,15 @@ jk_brick_kernel(const BrickArgs a)
 #pragma unroll
                             for (int i = 0; i < NFI; i++)
 #pragma unroll
-                            for (int l = 0; l < NFL; l++) s = fma(ERI_(i, j, k, l), d[i * NFL + l], s);
+                            for (int l = 0; l < NFL; l++) {
+                                const double d = P::DI_SMEM ? SLOT_(P::S_DI + NFI * NFK + i * NFL + l)
+                                                            : __ldg(dm + (size_t)(i0 + i) * nao + l0 + l);
+                                s = fma(ERI_(i, j, k, l), d, s);
+                            }
                             if (live) atomicAdd(a.vk + (size_t)(j0 + j) * nao + k0 + k, s);
                         }
                     }
                     {   // K_jl += sum_ik (ij|kl) D[i,k]: scattered per quartet
-                        double d[NFI * NFK];
-#pragma unroll
-                        for (int i = 0; i < NFI; i++)
-#pragma unroll
-                        for (int k = 0; k < NFK; k++) d[i * NFK + k] = __ldg(dm + (size_t)(i0 + i) * nao + k0 + k);
 #pragma unroll
                         for (int j = 0; j < NFJ; j++)
 #pragma unroll
@@ -389,7 +440,11 @@ jk_brick_kernel(const BrickArgs a)
 #pragma unroll
                             for (int i = 0; i < NFI; i++)
 #pragma unroll
-                            for (int k = 0; k < NFK; k++) s = fma(ERI_(i, j, k, l), d[i * NFK + k], s);
+                            for (int k = 0; k < NFK; k++) {
+                                const double d = P::DI_SMEM ? SLOT_(P::S_DI + i * NFK + k)
+                                                            : __ldg(dm + (size_t)(i0 + i) * nao + k0 + k);
+                                s = fma(ERI_(i, j, k, l), d, s);
+                            }
                             if (live) atomicAdd(a.vk + (size_t)(j0 + j) * nao + l0 + l, s);
                         }
                     }
@@ -403,15 +458,15 @@ jk_brick_kernel(const BrickArgs a)
                     for (int i = 0; i < NFI; i++)
 #pragma unroll
                     for (int k = 0; k < NFK; k++) {
-                        const double v = P::ACC_SMEM ? sacc[(i * NFK + k) * 32] : kacc[(P::ACC_SMEM ? 0 : i * NFK + k)];
+                        const double v = P::ACC_SMEM ? SLOT_(P::S_ACC + i * NFK + k) : kacc[P::ACC_SMEM ? 0 : i * NFK + k];
                         atomicAdd(a.vk + (size_t)(i0 + i) * nao + k0 + k, v);
                     }
 #pragma unroll
                     for (int i = 0; i < NFI; i++)
 #pragma unroll
                     for (int l = 0; l < NFL; l++) {
-                        const double v = P::ACC_SMEM ? sacc[(NFI * NFK + i * NFL + l) * 32]
-                                                     : kacc[(P::ACC_SMEM ? 0 : NFI * NFK + i * NFL + l)];
+                        const double v = P::ACC_SMEM ? SLOT_(P::S_ACC + NFI * NFK + i * NFL + l)
+                                                     : kacc[P::ACC_SMEM ? 0 : NFI * NFK + i * NFL + l];
                         atomicAdd(a.vk + (size_t)(i0 + i) * nao + l0 + l, v);
                     }
                 }
@@ -427,6 +482,7 @@ jk_brick_kernel(const BrickArgs a)
             }
         }
     }
+#undef SLOT_
     if (lane == 0 && nq) atomicAdd(a.qcount, nq);
 }
 

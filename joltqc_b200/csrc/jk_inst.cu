@@ -72,7 +72,7 @@ static cudaError_t launch_brick(const BrickArgs& a, int nsm, cudaStream_t st)
 {
     using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
     using P = BrickPlan<JQC_LI, JQC_LJ, LK, LL>;
-    if constexpr (S::N <= JQC_SMALL_N && P::FITS) {
+    if constexpr (P::FITS) {
         auto kern = jk_brick_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K>;
         static std::atomic<int> cache[JQC_MAX_DEVICES];
         int blocks_per_sm = 1;

@@ -38,17 +38,7 @@ inline cudaError_t jk_launch(int li, int lj, int lk, int ll, int variant, const 
     return cudaErrorInvalidValue;
 }
 
-// Classes that run on the brick kernel (jk_brick.cuh): integral block in one thread's registers and
-// the per-i K accumulators within the shared-memory budget.  Mirrors BrickPlan<>.
-inline bool jk_brick_supported(int li, int lj, int lk, int ll)
-{
-    auto nf = [](int l) { return (l + 1) * (l + 2) / 2; };
-    const int n = nf(li) * nf(lj) * nf(lk) * nf(ll);
-    if (n > JQC_SMALL_N_VALUE) return false;
-    const int nki = nf(li) * (nf(lk) + nf(ll)), njkl = nf(lk) * nf(ll);
-    const bool acc_smem = (n + nki + njkl > 80) && nki > 12;
-    return !acc_smem || (size_t)2 * 4 * 32 * nki * sizeof(double) <= 200 * 1024;   // 2 CTAs of 4 warps at 255 registers
-}
+// Classes that run on the brick kernel: brick_shape(li, lj, lk, ll).fits (jk_brick.cuh).
 
 inline cudaError_t jk_brick_launch(int li, int lj, int lk, int ll, int variant, const BrickArgs& a, int nsm, cudaStream_t st)
 {

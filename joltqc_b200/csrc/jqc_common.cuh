@@ -118,4 +118,100 @@ __device__ __forceinline__ void rys_roots(double x, double* __restrict__ rw)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Shared-memory copy of the NROOTS block of the Chebyshev table.  The per-lane interval gathers of
+// rys_roots (14 coefficient pairs per root, a different interval in every lane) saturate the
+// L1/TEX path when they go to global memory (profiles/r2: 31 % of the stall samples of the
+// (ps|ps) class); from shared memory the same gathers are 16-byte LDS with rows padded to 15
+// quad-words, so that 8 different intervals fall into 8 different bank groups.
+template <int NROOTS>
+struct RysSmem {
+    static constexpr int NINT = 14 + 2 * NROOTS;         // intervals of width 2.5 below x = 35 + 5 n
+    static constexpr int ROW = RYS_NCOEF + 1;            // padded row (quad-words)
+    static constexpr int QUADS = NROOTS * NINT * ROW;
+    static constexpr size_t BYTES = (size_t)QUADS * sizeof(double2);
+};
+
+template <int NROOTS>
+__device__ __forceinline__ void rys_table_to_smem(double2* __restrict__ s_tab)
+{
+    using T = RysSmem<NROOTS>;
+    const double2* __restrict__ src = reinterpret_cast<const double2*>(RYS_CHEB + RYS_CHEB_OFFSET[NROOTS - 1]);
+    for (int idx = threadIdx.x; idx < NROOTS * T::NINT * RYS_NCOEF; idx += blockDim.x) {
+        const int k = idx % RYS_NCOEF, row = idx / RYS_NCOEF;
+        const int it = row / NROOTS, i = row - it * NROOTS;
+        s_tab[(i * T::NINT + it) * T::ROW + k] = src[idx];
+    }
+    __syncthreads();
+}
+
+template <int NROOTS>
+__device__ __forceinline__ void rys_roots_smem(double x, double* __restrict__ rw, const double2* __restrict__ s_tab)
+{
+    using T = RysSmem<NROOTS>;
+    constexpr int TRI = NROOTS * (NROOTS - 1) / 2;
+    constexpr double large_x = NROOTS * 5 + 35;
+    if (x >= large_x) {
+        const double inv_x = 1.0 / x;
+        const double t = SQRTPIE4 * sqrt(inv_x);
+#pragma unroll
+        for (int i = 0; i < NROOTS; i++) {
+            rw[2 * i] = RYS_LARGEX[(TRI + i) * 2] * inv_x;
+            rw[2 * i + 1] = RYS_LARGEX[(TRI + i) * 2 + 1] * t;
+        }
+        return;
+    }
+    const int it = (int)(x * 0.4);
+    const double u = fma(x - it * 2.5, 0.8, -1.0);
+    const double u2 = 2.0 * u;
+    const double2* __restrict__ blk = s_tab + it * T::ROW;
+#pragma unroll
+    for (int i = 0; i < NROOTS; i++) {
+        const double2* __restrict__ c = blk + i * T::NINT * T::ROW;
+        double2 a = c[RYS_NCOEF - 1];
+        double r1 = a.x, w1 = a.y, r2 = 0.0, w2 = 0.0;
+#pragma unroll
+        for (int k = RYS_NCOEF - 2; k >= 1; k--) {
+            a = c[k];
+            const double r0 = fma(u2, r1, a.x) - r2;
+            const double w0 = fma(u2, w1, a.y) - w2;
+            r2 = r1; r1 = r0;
+            w2 = w1; w1 = w0;
+        }
+        a = c[0];
+        rw[2 * i] = fma(u, r1, a.x) - r2;
+        rw[2 * i + 1] = fma(u, w1, a.y) - w2;
+    }
+}
+
+// Sum N per-lane values over the 32 lanes of a warp with a reduce-scatter butterfly: each step
+// halves the number of values a lane still carries (N/2 + N/4 + ... shuffles in total instead of
+// 5 N for independent butterflies).  On return a lane holds in v[0 .. cnt) the warp totals of the
+// elements start .. start + cnt - 1 (cnt <= warp_rs_final(N); the other slots are padding).
+__host__ __device__ constexpr int warp_rs_final(int n)
+{
+    for (int s = 0; s < 5; s++) n = (n + 1) / 2;
+    return n;
+}
+
+template <int N, int OFF>
+struct WarpReduceScatter {
+    static __device__ __forceinline__ void run(double* __restrict__ v, const int lane, int& start, int& cnt)
+    {
+        constexpr int H = (N + 1) / 2;
+        const bool up = (lane & OFF) != 0;
+#pragma unroll
+        for (int e = 0; e < H; e++) {
+            const double lo = v[e];
+            const double hi = (e + H < N) ? v[e + H] : 0.0;
+            const double send = up ? lo : hi;
+            const double keep = up ? hi : lo;
+            v[e] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        if (up) { start += H; cnt -= H; }
+        else cnt = cnt < H ? cnt : H;
+        if constexpr (OFF > 1) WarpReduceScatter<H, OFF / 2>::run(v, lane, start, cnt);
+    }
+};
+
 }  // namespace jqc
