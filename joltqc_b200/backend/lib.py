@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libjoltqc_b200.so")
+# JQC_LIB_PATH selects another build of the same library (A/B experiments with tools/tune_*.py)
+LIB_PATH = os.environ.get("JQC_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libjoltqc_b200.so")
 
 EXPORTS = [
     "jqc_engine_create", "jqc_engine_destroy", "jqc_last_error", "jqc_engine_set_shard", "jqc_q_matrix",

@@ -30,13 +30,16 @@ def _run(cmd):
     return r.stderr
 
 
-def build(force=False, verbose=False, jobs=None, extra_flags=None):
+def build(force=False, verbose=False, jobs=None, extra_flags=None, out=None, objdir=None):
     """extra_flags: e.g. ["-DJQC_WARP_FORCE_ACC=40", "-DJQC_WARP_FORCE_REGS=168"] for a tuning build
     (forces a full rebuild; see tools/tune_warp.py)."""
-    global FLAGS
+    global FLAGS, OBJ, LIB
     if extra_flags:
         FLAGS = FLAGS + list(extra_flags)
         force = True
+    if out:       # variant build: own output file and object directory
+        LIB = os.path.abspath(out)
+        OBJ = objdir or (OBJ + "_" + os.path.splitext(os.path.basename(out))[0])
     os.makedirs(OBJ, exist_ok=True)
     stamp = _newest_src()
     todo = []
@@ -63,4 +66,6 @@ def build(force=False, verbose=False, jobs=None, extra_flags=None):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True, extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose=True, extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")],
+                out=outs[0] if outs else None))

@@ -117,6 +117,12 @@ struct jqc_engine {
     // molecules exercise the multi-chunk loops
     size_t queue_cap = QUEUE_CAP;
     int kl_chunk_max = 2048;
+    // brick launches need no queue: they go round-robin to auxiliary streams so that the tail of one
+    // launch overlaps the start of the next (and the quartet-list launches of the main stream)
+    static constexpr int NAUX = 2;
+    cudaStream_t aux[NAUX] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr};
+    int use_aux = 1;
     // state of the last build
     int last_n = 0, last_neff = 0, last_hermi = 1, last_j = 0, last_k = 0, launches = 0;
     bool built = false, profiling = false;
@@ -146,6 +152,7 @@ extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine
     if (const char* m = getenv("JQC_SMALL_TILES")) e->small_tiles = atoi(m) != 0;
     if (const char* m = getenv("JQC_BRICK")) e->use_brick = atoi(m) != 0;
     if (const char* m = getenv("JQC_BRICK_ICHUNK")) e->brick_ichunk = std::max(1, atoi(m));
+    if (const char* m = getenv("JQC_AUX_STREAMS")) e->use_aux = atoi(m) != 0;
     if (const char* m = getenv("JQC_QUEUE_CAP")) e->queue_cap = std::min<size_t>(QUEUE_CAP, std::max<size_t>(256, (size_t)atoll(m)));
     if (const char* m = getenv("JQC_KL_CHUNK")) e->kl_chunk_max = std::max(1, atoi(m));
     cudaDeviceProp prop;
@@ -243,6 +250,11 @@ extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine
     CU(e->d_child_list.upload(clist));
     if ((size_t)d->nbas * sizeof(float) > 48 * 1024)   // dm_pool_kernel keeps one row of shell maxima in shared memory
         CU(cudaFuncSetAttribute(dm_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(d->nbas * sizeof(float))));
+    for (int i = 0; i < jqc_engine::NAUX; i++) {
+        CU(cudaStreamCreateWithFlags(&e->aux[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CU(e->d_logmax.ensure(1));
     CU(e->d_nact.ensure(e->npairs()));
     CU(e->d_counters.ensure(MAX_CHUNKS));
@@ -256,6 +268,11 @@ extern "C" void jqc_engine_destroy(jqc_engine* e)
     if (!e) return;
     cudaSetDevice(e->device);
     for (auto ev : e->ev) cudaEventDestroy(ev);
+    for (int i = 0; i < jqc_engine::NAUX; i++) {
+        if (e->aux[i]) cudaStreamDestroy(e->aux[i]);
+        if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     delete e;
 }
 
@@ -503,6 +520,12 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
     e->launches = 0;
     size_t nev = 0;
     bool queue_ready = false;
+    const bool fork = e->use_aux && !e->profiling;
+    int n_brick = 0;
+    if (fork) {
+        CU(cudaEventRecord(e->ev_fork, st));
+        for (int i = 0; i < jqc_engine::NAUX; i++) CU(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
+    }
     for (int gi = e->ngroups - 1; gi >= 0; gi--)
     for (int gj = gi; gj >= 0; gj--)
     for (int gk = gi; gk >= 0; gk--)
@@ -553,7 +576,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
                 e0 = e->ev[nev++]; e1 = e->ev[nev++];
                 CU(cudaEventRecord(e0, st));
             }
-            CU(jk_brick_launch(li, lj, lk, ll, variant, b, e->nsm, st));
+            CU(jk_brick_launch(li, lj, lk, ll, variant, b, e->nsm, fork ? e->aux[n_brick++ % jqc_engine::NAUX] : st));
             if (e->profiling) CU(cudaEventRecord(e1, st));
             e->launches += 1;
             e->chunks.push_back({key, pw});
@@ -621,6 +644,12 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             if (e->profiling) CU(cudaEventRecord(e1, st));
             e->launches += 2;
             e->chunks.push_back({key, pw});
+        }
+    }
+    if (fork) {
+        for (int i = 0; i < jqc_engine::NAUX; i++) {
+            CU(cudaEventRecord(e->ev_join[i], e->aux[i]));
+            CU(cudaStreamWaitEvent(st, e->ev_join[i], 0));
         }
     }
     e->last_n = n_dm; e->last_neff = neff; e->last_hermi = hermi; e->last_j = with_j; e->last_k = with_k;

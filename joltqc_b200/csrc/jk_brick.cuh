@@ -54,21 +54,51 @@ struct BrickArgs {
     unsigned long long* __restrict__ qcount;  // evaluated quartets (accounting)
 };
 
+// Primitive-pair data of the bra pair (i,j) of a step, staged in shared memory once per warp
+// (the pair is the same for all 32 lanes): 8 doubles per primitive pair.  Lane p < npi*npj
+// evaluates pair p (one exp + one division each, in parallel) instead of every lane repeating
+// all of them inside its primitive loops.
+constexpr int BRA_PRIM_DOUBLES = NPRIM_MAX * NPRIM_MAX * 8;
+
+__device__ __forceinline__ void stage_bra_prims(double* __restrict__ s_bra, const double* __restrict__ bi,
+                                                const double* __restrict__ bj, const double4 ri, const double4 rj,
+                                                const int npi, const int npj, const int lane)
+{
+    __syncwarp();                                   // readers of the previous step are done
+    if (lane < npi * npj) {
+        const int ip = lane / npj, jp = lane - ip * npj;
+        const double2 cei = *reinterpret_cast<const double2*>(bi + 4 + 2 * ip);
+        const double2 cej = *reinterpret_cast<const double2*>(bj + 4 + 2 * jp);
+        const double dx = rj.x - ri.x, dy = rj.y - ri.y, dz = rj.z - ri.z;
+        const double rr_ij = dx * dx + dy * dy + dz * dz;
+        const double aij = cei.y + cej.y;
+        const double inv_aij = 1.0 / aij;
+        const double aj_aij = cej.y * inv_aij;
+        double* o = s_bra + lane * 8;
+        o[0] = aij;
+        o[1] = inv_aij;
+        o[2] = aj_aij;
+        o[3] = cei.x * cej.x * exp(-cei.y * aj_aij * rr_ij);
+        o[4] = fma(dx, aj_aij, ri.x);
+        o[5] = fma(dy, aj_aij, ri.y);
+        o[6] = fma(dz, aj_aij, ri.z);
+    }
+    __syncwarp();
+}
+
 // One shell quartet, all in registers: eri[N] += contracted integrals (reference: 1q1t.cu:86-405).
 template <int LI, int LJ, int LK, int LL>
-__device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const double* __restrict__ bi,
-                                               const double* __restrict__ bj, const double* __restrict__ bk,
-                                               const double* __restrict__ bl, const double4 ri, const double4 rj,
-                                               const double4 rk, const double4 rl, const int npi, const int npj,
-                                               const int npk, const int npl, const double omega, const double fac,
-                                               const double2* __restrict__ s_rys)
+__device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const double* __restrict__ s_bra,
+                                               const double* __restrict__ bk, const double* __restrict__ bl,
+                                               const double4 ri, const double4 rj, const double4 rk, const double4 rl,
+                                               const int npij, const int npk, const int npl, const double omega,
+                                               const double fac, const double2* __restrict__ s_rys)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
     constexpr int NROOTS = S::NROOTS, GS = S::GSIZE, DJ = S::DJ, DK = S::DK, DL = S::DL;
     const double rjri[3] = {rj.x - ri.x, rj.y - ri.y, rj.z - ri.z};
     const double rlrk[3] = {rl.x - rk.x, rl.y - rk.y, rl.z - rk.z};
-    const double rr_ij = rjri[0] * rjri[0] + rjri[1] * rjri[1] + rjri[2] * rjri[2];
     const double rr_kl = rlrk[0] * rlrk[0] + rlrk[1] * rlrk[1] + rlrk[2] * rlrk[2];
 #pragma unroll
     for (int n = 0; n < N; n++) eri[n] = 0.0;
@@ -84,17 +114,12 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
         const double ckcl = cek.x * cel.x * exp(-cek.y * al_akl * rr_kl);
         const double qx = fma(rlrk[0], al_akl, rk.x), qy = fma(rlrk[1], al_akl, rk.y), qz = fma(rlrk[2], al_akl, rk.z);
 #pragma unroll 1
-        for (int ip = 0; ip < npi; ip++)
-#pragma unroll 1
-        for (int jp = 0; jp < npj; jp++) {
-            const double2 cei = *reinterpret_cast<const double2*>(bi + 4 + 2 * ip);
-            const double2 cej = *reinterpret_cast<const double2*>(bj + 4 + 2 * jp);
-            const double aij = cei.y + cej.y;
-            const double inv_aij = 1.0 / aij;
-            const double aj_aij = cej.y * inv_aij;
-            const double cicj = fac * cei.x * cej.x * exp(-cei.y * aj_aij * rr_ij);
-            const double Rpq[3] = {fma(rjri[0], aj_aij, ri.x) - qx, fma(rjri[1], aj_aij, ri.y) - qy,
-                                   fma(rjri[2], aj_aij, ri.z) - qz};
+        for (int ipj = 0; ipj < npij; ipj++) {
+            const double4 b0 = *reinterpret_cast<const double4*>(s_bra + ipj * 8);
+            const double4 b1 = *reinterpret_cast<const double4*>(s_bra + ipj * 8 + 4);
+            const double aij = b0.x, inv_aij = b0.y, aj_aij = b0.z;
+            const double cicj = fac * b0.w;
+            const double Rpq[3] = {b1.x - qx, b1.y - qy, b1.z - qz};
             const double rr = Rpq[0] * Rpq[0] + Rpq[1] * Rpq[1] + Rpq[2] * Rpq[2];
             const double inv_aijkl = 1.0 / (aij + akl);
             const double theta = aij * akl * inv_aijkl;
@@ -174,7 +199,7 @@ __host__ __device__ constexpr BrickShape brick_shape(int li, int lj, int lk, int
     b.regs = live <= 12 ? 128 : (live <= 36 ? 168 : 255);
     b.minb = 65536 / (b.regs * b.nwarps * 32);
     b.rys_bytes = (size_t)b.nroots * (14 + 2 * b.nroots) * (RYS_NCOEF + 1) * 16;
-    b.smem = b.rys_bytes + (size_t)b.nwarps * 32 * b.slots * sizeof(double);
+    b.smem = b.rys_bytes + (size_t)b.nwarps * (BRA_PRIM_DOUBLES + 32 * b.slots) * sizeof(double);
     b.fits = b.n <= JQC_SMALL_N && b.smem * b.minb <= 216 * 1024;
     return b;
 }
@@ -209,8 +234,10 @@ jk_brick_kernel(const BrickArgs a)
     // shared memory: [Rys table of this class][lane-private slots: element-major, lane-minor]
     const double2* __restrict__ s_rys = brick_smem;
     rys_table_to_smem<S::NROOTS>(brick_smem);
-    double* __restrict__ slot = reinterpret_cast<double*>(brick_smem) + P::RYS_BYTES / sizeof(double) +
-                                (size_t)warp * 32 * P::SLOTS + lane;
+    double* __restrict__ s_bra = reinterpret_cast<double*>(brick_smem) + P::RYS_BYTES / sizeof(double) +
+                                 (size_t)warp * (BRA_PRIM_DOUBLES + 32 * P::SLOTS);
+    double* __restrict__ slot = s_bra + BRA_PRIM_DOUBLES + lane;
+    const int npij = a.npi * a.npj;
 #define SLOT_(x) slot[(x) * 32]
     unsigned long long nq = 0;
 
@@ -328,9 +355,9 @@ jk_brick_kernel(const BrickArgs a)
                 if (ish == jsh) fac *= 0.5;
                 if (ksh == lsh) fac *= 0.5;
                 if (ish == ksh && jsh == lsh) fac *= 0.5;
+                stage_bra_prims(s_bra, bi, bj, ri, rj, a.npi, a.npj, lane);
                 double eri[N];
-                eri_block_regs<LI, LJ, LK, LL>(eri, bi, bj, bk, bl, ri, rj, rk, rl, a.npi, a.npj, a.npk, a.npl,
-                                               a.omega, fac, s_rys);
+                eri_block_regs<LI, LJ, LK, LL>(eri, s_bra, bk, bl, ri, rj, rk, rl, npij, a.npk, a.npl, a.omega, fac, s_rys);
 #define ERI_(i, j, k, l) eri[(((i) * NFJ + (j)) * NFK + (k)) * NFL + (l)]
                 if constexpr (DO_J) {
                     // J_kl += sum_ij (ij|kl) D[j,i]: lane-stationary

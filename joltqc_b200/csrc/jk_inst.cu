@@ -37,7 +37,9 @@ static cudaError_t blocks_per_sm_cached(std::atomic<int>* cache, K kern, int thr
     return cudaSuccess;
 }
 
-// Multi-lane kernel: warps per block chosen so that two blocks fit the 227 KB of an SM when possible.
+// Multi-lane kernel: warps per block chosen so that several blocks fit the 227 KB of an SM.  (A
+// shared-memory copy of the Rys table with one big block per SM was measured and lost ~6 % here:
+// the roots are < 5 % of this kernel's stall samples, the table costs occupancy; profiles/r2.)
 template <int LK, int LL>
 struct WarpCfg {
     using P = WarpPlan<JQC_LI, JQC_LJ, LK, LL>;

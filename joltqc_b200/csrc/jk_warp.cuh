@@ -18,6 +18,9 @@
 
 namespace jqc {
 
+// conflict-minimising strides per class (generated: tools/gen_warp_layout.py)
+#include "jk_warp_layout.h"
+
 // 8-byte asynchronous global->shared copy (LDGSTS): the density blocks of a quartet are fetched
 // while the lanes are busy with the recurrences and products, without holding registers.
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src)
@@ -60,6 +63,104 @@ __device__ __forceinline__ void rys_root_one(double x, int i, double& root, doub
     weight = fma(u, w1, a.y) - w2;
 }
 
+// Same, from the shared-memory copy of the table (RysSmem layout, jqc_common.cuh).
+template <int NROOTS>
+__device__ __forceinline__ void rys_root_one_smem(double x, int i, double& root, double& weight,
+                                                  const double2* __restrict__ s_tab)
+{
+    using T = RysSmem<NROOTS>;
+    constexpr int TRI = NROOTS * (NROOTS - 1) / 2;
+    constexpr double large_x = NROOTS * 5 + 35;
+    if (x >= large_x) {
+        const double inv_x = 1.0 / x;
+        root = RYS_LARGEX[(TRI + i) * 2] * inv_x;
+        weight = RYS_LARGEX[(TRI + i) * 2 + 1] * (SQRTPIE4 * sqrt(inv_x));
+        return;
+    }
+    const int it = (int)(x * 0.4);
+    const double u = fma(x - it * 2.5, 0.8, -1.0);
+    const double u2 = 2.0 * u;
+    const double2* __restrict__ c = s_tab + (i * T::NINT + it) * T::ROW;
+    double2 a = c[RYS_NCOEF - 1];
+    double r1 = a.x, w1 = a.y, r2 = 0.0, w2 = 0.0;
+#pragma unroll
+    for (int k = RYS_NCOEF - 2; k >= 1; k--) {
+        a = c[k];
+        const double r0 = fma(u2, r1, a.x) - r2;
+        const double w0 = fma(u2, w1, a.y) - w2;
+        r2 = r1; r1 = r0;
+        w2 = w1; w1 = w0;
+    }
+    a = c[0];
+    root = fma(u, r1, a.x) - r2;
+    weight = fma(u, w1, a.y) - w2;
+}
+
+// TRR + HRR for one cartesian direction with the recurrences in REGISTERS: the TRR runs row by row
+// over k (two rows of li+lj+1 values live), every finished row goes through the (i -> j) HRR and
+// is stored once; the (k -> l) HRR then reads each (i,j) column back once.  Shared-memory traffic
+// is ~1 access per recurrence step instead of 3 for the in-place form below, and the dependent
+// chains run at register latency.
+template <int LI, int LJ, int LK, int LL>
+__device__ __forceinline__ void fill_g_dir_regs(double* __restrict__ gd, const double seed, const double c0, const double cp,
+                                                const double b10, const double b01, const double b00, const double ab,
+                                                const double cd)
+{
+    using S = QuartetShape<LI, LJ, LK, LL>;
+    constexpr int DJ = S::DJ, DK = WarpLayout<LI, LJ, LK, LL>::DKP, DL = DK * (LK + 1), LIJ = S::LIJ, LKL = S::LKL;
+    double prev[LIJ + 1], cur[LIJ + 1];
+#pragma unroll
+    for (int k = 0; k <= LKL; k++) {
+        // row k of the TRR table g(i, 0 | k, 0)
+        double row[LIJ + 1];
+        if (k == 0) {
+            row[0] = seed;
+            if constexpr (LIJ > 0) row[1] = c0 * seed;
+#pragma unroll
+            for (int i = 1; i < LIJ; i++) row[i + 1] = fma(c0, row[i], (i * b10) * row[i - 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i <= LIJ; i++) {
+                double v = cp * cur[i];
+                if (k > 1) v = fma((k - 1) * b01, prev[i], v);
+                if (i > 0) v = fma(i * b00, cur[i - 1], v);
+                row[i] = v;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i <= LIJ; i++) { prev[i] = cur[i]; cur[i] = row[i]; }
+        // (i -> j) HRR of this row, levels j = 0 .. LJ; level j keeps i <= LIJ - j
+#pragma unroll
+        for (int j = 0; j <= LJ; j++) {
+#pragma unroll
+            for (int i = 0; i <= LI; i++) gd[i + j * DJ + k * DK] = row[i];
+            if (j < LJ) {
+#pragma unroll
+                for (int i = 0; i < LIJ - j; i++) row[i] = fma(-ab, row[i], row[i + 1]);
+            }
+        }
+    }
+    if constexpr (LL > 0) {
+        // (k -> l) HRR per (i,j) column
+#pragma unroll
+        for (int j = 0; j <= LJ; j++)
+#pragma unroll
+        for (int i = 0; i <= LI; i++) {
+            const int ij = i + j * DJ;
+            double v[LKL + 1];
+#pragma unroll
+            for (int k = 0; k <= LKL; k++) v[k] = gd[ij + k * DK];
+#pragma unroll
+            for (int l = 1; l <= LL; l++) {
+#pragma unroll
+                for (int k = 0; k <= LKL - l; k++) v[k] = fma(-cd, v[k], v[k + 1]);
+#pragma unroll
+                for (int k = 0; k <= LK; k++) gd[ij + k * DK + l * DL] = v[k];
+            }
+        }
+    }
+}
+
 // TRR + in-place HRR for one cartesian direction into gd[GSIZE] (shared memory).
 template <int LI, int LJ, int LK, int LL>
 __device__ __forceinline__ void fill_g_dir(double* __restrict__ gd, const double seed, const double c0, const double cp,
@@ -70,7 +171,7 @@ __device__ __forceinline__ void fill_g_dir(double* __restrict__ gd, const double
     // different lanes read in the product phase fall into different banks; DL keeps the exact
     // (LK+1)*DK aliasing the in-place HRR relies on.
     using S = QuartetShape<LI, LJ, LK, LL>;
-    constexpr int DJ = S::DJ, DK = S::DK | 1, DL = DK * (LK + 1), LIJ = S::LIJ, LKL = S::LKL;
+    constexpr int DJ = S::DJ, DK = WarpLayout<LI, LJ, LK, LL>::DKP, DL = DK * (LK + 1), LIJ = S::LIJ, LKL = S::LKL;
     gd[0] = seed;
     if constexpr (LIJ > 0) {
         double s0 = seed, s1 = c0 * seed;
@@ -185,7 +286,7 @@ struct WarpPlan {
     static constexpr int T = lanes();
     static constexpr int QPW = 32 / T;
     static constexpr int NKLP = (NKL + T - 1) / T;
-    static constexpr int DKP = S::DK | 1, DLP = DKP * (LK + 1), GSP = DLP * (LL + 1);
+    static constexpr int DKP = WarpLayout<LI, LJ, LK, LL>::DKP, DLP = DKP * (LK + 1), GSP = DLP * (LL + 1);
     static constexpr int IS = GSP | 1;                  // stride between (root, direction) arrays: odd
     static constexpr int G_ALL = S::NROOTS * 3 * IS;
     static constexpr int NDBLK = NIJ + NKL + S::NFJ * S::NFL + S::NFJ * S::NFK + S::NFI * S::NFL + S::NFI * S::NFK;
@@ -197,13 +298,14 @@ struct WarpPlan {
     static constexpr int OFF_D = OFF_G + (ALIAS ? (G_ALL > STAGE ? G_ALL : STAGE) : G_ALL);
     static constexpr int OFF_STAGE = ALIAS ? OFF_G : OFF_D + NDBLK;
     static constexpr int END = ALIAS ? OFF_D + NDBLK : OFF_STAGE + STAGE;
-    // stride between quartet groups: congruent to T*IS mod 16 doubles, so that lane (group g, t)
-    // of a warp sees offset (g*T + t)*IS mod 16 — the 16 lanes of a half-warp then fall into 16
-    // different 8-byte bank pairs whenever they address "own slot + common offset"
+    // stride between quartet groups, modulo 16 doubles (= all 32 banks): the value of the generated
+    // layout table, which minimises the bank conflicts of the product-phase loads (lane (g, t) reads
+    // slot(t) of group g); without an entry, T*IS mod 16 (own-slot accesses conflict-free)
     static constexpr int per_group()
     {
+        constexpr int want = WarpLayout<LI, LJ, LK, LL>::PG16 >= 0 ? WarpLayout<LI, LJ, LK, LL>::PG16 : (T * IS) % 16;
         int pg = END;
-        while ((pg - T * IS) % 16 != 0) pg++;
+        while (pg % 16 != want) pg++;
         return pg;
     }
     static constexpr int PER_GROUP = per_group();
@@ -405,7 +507,11 @@ jk_warp_kernel(const JKArgs a)
                             const double seed = d == 0 ? ckcl : (d == 1 ? gy0 : wt);
                             const double c0 = fma(ab, aj_aij, -rt_aij * pq);
                             const double cp = fma(cd, al_akl, rt_akl * pq);
+#ifdef JQC_WARP_SMEM_RECURRENCE
                             fill_g_dir<LI, LJ, LK, LL>(s_g + (size_t)item * GS, seed, c0, cp, b10, b01, b00, ab, cd);
+#else
+                            fill_g_dir_regs<LI, LJ, LK, LL>(s_g + (size_t)item * GS, seed, c0, cp, b10, b01, b00, ab, cd);
+#endif
                         }
                     }
                     __syncwarp();

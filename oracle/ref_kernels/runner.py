@@ -136,7 +136,7 @@ class RefJK:
                 pairs[i, j] = tij[mask][order].contiguous()
         return pairs
 
-    def get_jk_raw(self, dm_kern, hermi=1, cutoff=1e-13, time_it=False):
+    def get_jk_raw(self, dm_kern, hermi=1, cutoff=1e-13, time_it=False, time_classes=False):
         """dm_kern: (nao, nao) kernel-side density (one matrix, hermi = 1).  Returns the raw
         accumulators (vj, vk) of the kernels, i.e. before jk.py:353-370."""
         assert hermi == 1 and dm_kern.dim() == 2
@@ -162,6 +162,7 @@ class RefJK:
         tasks = [(i, j, k, l) for i in range(n) for j in range(i + 1) for k in range(i + 1) for l in range(k + 1)]
         nquartets = 0
         launches = 0
+        class_events = []
         i32, f32, f64, vp = ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
         for (i, j, k, l) in tasks[::-1]:
             if (i, j) not in tile_pairs or (k, l) not in tile_pairs:
@@ -188,13 +189,26 @@ class RefJK:
                     n64 = self.queue_depth - offset
                     launches += 1
                     if n64 > 0:
+                        if time_classes:
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0.record()
                         RefKernels.launch(fn, ((n64 + nsq - 1) // nsq,), tuple(ent["block"]), ent["shared_mem"], stream,
                                           (self.nao, self.basis.data_ptr(), dms.data_ptr(), vj.data_ptr(), vk.data_ptr(), 0.0,
                                            self.queue.data_ptr() + offset * 8, int(n64)),
                                           (i32, vp, vp, vp, vp, f64, vp, i32))
+                        if time_classes:
+                            e1.record()
+                            class_events.append((name[3:7], e0, e1, n64))
                         launches += 1
                         nquartets += n64
         self.last = {"quartets": nquartets, "launches": launches}
+        if time_classes:
+            torch.cuda.synchronize()
+            cm = {}
+            for cls, e0, e1, nq in class_events:
+                ms, q = cm.get(cls, (0.0, 0))
+                cm[cls] = (ms + e0.elapsed_time(e1), q + nq)
+            self.last["class_ms"] = cm
         if time_it:
             ev1.record()
             torch.cuda.synchronize()

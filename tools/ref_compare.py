@@ -18,6 +18,12 @@ print("missing kernels:", len(ref.missing_kernels()))
 dk = eng.dm_from_mol(dm)
 t0 = time.perf_counter(); rj, rk = ref.get_jk_raw(dk, time_it=True); print("ref warm-up", ref.last, time.perf_counter() - t0)
 rj, rk = ref.get_jk_raw(dk, time_it=True); print("ref timed", ref.last)
+if len(sys.argv) > 3:
+    ref.get_jk_raw(dk, time_classes=True)
+    with open(sys.argv[3], "w") as f:
+        f.write("class,ms,quartets\n")
+        for cls, (ms, q) in sorted(ref.last["class_ms"].items(), key=lambda kv: -kv[1][0]):
+            f.write("(%s|%s),%.3f,%d\n" % (cls[:2], cls[2:], ms, q))
 for rep in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     buf = eng.build_partial(dm, hermi=1)
