@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the FP64 direct-SCF J/K build (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME] [--dm ones|decay]
+    python bench.py --gpus N --steps K --warmup W [--impl reference|jqc-kernels] [--workload NAME] [--dm ones|decay]
 
 A "step" is one get_jk (J and K, hermi=1, cutoff 1e-13) of the workload.  Default workload:
 config 4 of BASELINE.json — valinomycin/def2-TZVP, represented by the in-tree stand-in
@@ -11,9 +11,15 @@ D is synthetic: all ones, exactly what the reference's own J/K benchmark feeds
 
 Printed JSON (one line, rank 0): see the measurement contract in the task statement; `value`
 is seconds per J/K build with D resident in HBM (device-timed, max over ranks), `e2e` the
-same through the host-buffer C-ABI call, `roofline` the algorithmic FP64 FLOP/s of the build
-(SURVEY 8d model) against the FP64 FMA peak measured on the box, `cpu_baseline` the CPU
-restatement (oracle) on the host cores extrapolated from a bounded sample.
+same through the host-buffer C-ABI call (jqc_get_jk_host: pinned host D in, J and K out),
+`roofline` the algorithmic FP64 FLOP/s of the build (SURVEY 8d model) against the FP64 FMA
+peak measured on the box, `cpu_baseline` the CPU restatement (oracle) on the host cores
+extrapolated from a bounded sample (with one COMPLETE small build as the anchor of the
+extrapolation), `ref_kernels` the UNMODIFIED JoltQC kernels (oracle/_ref cubins) on the same GPU
+and the element-wise difference of the two results, `extra` the other BASELINE.json configs.
+
+--impl reference   : the CPU port alone (the reference's CPU path, libcint, is not installed).
+--impl jqc-kernels : the unmodified reference kernels alone (1 GPU).
 """
 import argparse
 import json
@@ -140,28 +146,80 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_baseline(lay, dm, budget_s=20.0):
+def cpu_port_baseline(lay, dm, budget_s=20.0, stride=None):
     """Time the CPU restatement on a bounded sample (every stride-th (ij) pair) and extrapolate."""
-    from oracle.oracle import OracleJK, lib
+    from oracle.oracle import OracleJK, use_all_cores
+    cores = use_all_cores()
     orc = OracleJK(lay)
-    cores = lib().oracle_num_threads()
     T = orc.transform()
     dmi = (T @ dm @ T.T)[None]
     t0 = time.perf_counter()
     orc.q_matrix(0.0)
     t_q = time.perf_counter() - t0
     npair = lay.nbasis * (lay.nbasis + 1) // 2
-    stride = max(1, npair // 400)
+    fixed = stride is not None
+    stride = stride or max(1, npair // 400)
     while True:
         t0 = time.perf_counter()
         orc.build_raw(dmi, 1, True, True, None, 1e-13, stride=stride, phase=stride // 2)
         dt = time.perf_counter() - t0
         nq = int(orc.last_nquartets)
-        if dt > budget_s / 4 or stride == 1:
+        if fixed or dt > budget_s / 4 or stride == 1:
             break
         stride = max(1, int(stride / min(8.0, max(2.0, budget_s / 2 / max(dt, 1e-3)))))
     return {"seconds_sample": dt, "quartets_sample": nq, "stride": stride, "cores": cores, "schwarz_seconds": t_q,
             "counts": orc.last_counts.copy()}
+
+
+def cpu_anchor():
+    """One COMPLETE (un-extrapolated) CPU build of benzene/cc-pVTZ next to its own sampled
+    extrapolation: how far the stride sampling used for the big workloads is off."""
+    from joltqc_b200.pyscf.basis import BasisLayout
+    mol, label = build_mol("benzene-ccpvtz")
+    lay = BasisLayout.from_mol(mol, alignment=4)
+    dm = make_dm(mol, "ones")
+    full = cpu_port_baseline(lay, dm, stride=1)
+    samp = cpu_port_baseline(lay, dm, stride=16)
+    return {"workload": label, "complete_build_s": full["seconds_sample"], "quartets": full["quartets_sample"],
+            "sampled_stride": samp["stride"], "extrapolated_s": samp["seconds_sample"] * samp["stride"],
+            "extrapolation_ratio": samp["seconds_sample"] * samp["stride"] / max(full["seconds_sample"], 1e-9)}
+
+
+def ref_kernels_leg(lay, eng, dm_dev, reps=1):
+    """Unmodified JoltQC kernels (oracle/_ref) on this GPU: seconds per build + element-wise
+    comparison of the kernel-side J/K accumulators with the engine's."""
+    import torch
+    try:
+        from oracle.ref_kernels import runner
+    except Exception as exc:           # cuda-python missing
+        return {"unavailable": "cuda-python runner not importable: %s" % exc}
+    if not runner.available():
+        return {"unavailable": "oracle/_ref not built (python -m oracle.ref_kernels.build_ref_kernels needs the reference tree)"}
+    ref = runner.RefJK(lay, eng)
+    missing = ref.missing_kernels()
+    if missing:
+        return {"unavailable": "oracle/_ref lacks %d kernels for this basis" % len(missing)}
+    dk = eng.dm_from_mol(dm_dev)
+    ref.get_jk_raw(dk)                                   # warm-up: loads the cubins
+    ts = []
+    for _ in range(reps):
+        rj, rk = ref.get_jk_raw(dk, time_it=True)
+        ts.append(ref.last["seconds"])
+    buf = eng.build_partial(dm_dev, hermi=1)
+    torch.cuda.synchronize()
+    n2 = lay.nao ** 2
+    vj, vk = buf[:n2].reshape(lay.nao, lay.nao), buf[n2:2 * n2].reshape(lay.nao, lay.nao)
+    counts, _, _ = eng.last_stats()
+    out = {"value": float(np.median(ts)), "unit": "s/iter", "kind": "unmodified JoltQC kernels (rys_1q1t_vjk / rys_1qnt_vjk / "
+           "screen_jk_tasks, A100 FP64 scheme table, reference driver loop with its blocking info reads), nvcc sm_100a "
+           "-std=c++17 --use_fast_math, launched through cuda-python",
+           "quartets": int(ref.last["quartets"]), "same_quartet_count": bool(int(counts.sum()) == ref.last["quartets"]),
+           "launches": int(ref.last["launches"]),
+           "max_abs_dJ_kernel_side": float((vj - rj).abs().max().item()), "max_abs_dK_kernel_side": float((vk - rk).abs().max().item()),
+           "max_abs_J": float(rj.abs().max().item()), "max_abs_K": float(rk.abs().max().item())}
+    del ref
+    torch.cuda.empty_cache()
+    return out
 
 
 _REAL_STDOUT = None
@@ -181,16 +239,80 @@ def _emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def _config(args, mol, lay, label, world):
+    return {"workload": label, "basis": WORKLOADS[args.workload][1], "nao": mol.nao, "nao_cart_kernel": lay.nao,
+            "shells": int((~lay.pad_id).sum()), "dm": args.dm, "hermi": 1, "with_j": True, "with_k": True,
+            "cutoff": 1e-13, "parallelism": f"static task interleave over {max(world, 1)} GPU(s) + 1 NCCL all_reduce",
+            "l2": "working set D+J+K = %.0f MB %s 126 MB L2, no explicit flush" % (3 * lay.nao**2 * 8 / 1e6, ">" if 3 * lay.nao**2 * 8 > 126e6 else "<")}
+
+
+def run_reference_arm(args, lay, dm, config):
+    """CPU port on all host cores: W untimed + K timed bounded samples of the same build."""
+    per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    first = cpu_port_baseline(lay, dm, budget_s=per_step)          # chooses the stride for the budget
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_port_baseline(lay, dm, stride=first["stride"])
+    ts, res = [], first
+    for _ in range(max(1, args.steps)):
+        res = cpu_port_baseline(lay, dm, stride=first["stride"])
+        ts.append(res["seconds_sample"])
+    est = float(np.mean(ts)) * res["stride"]
+    sample = (f"every {res['stride']}th (ij) shell pair of the same build ({res['quartets_sample']} quartets in "
+              f"{np.mean(ts):.2f} s per step), extrapolated x{res['stride']}")
+    _emit({"impl": "reference", "metric": "fp64_jk_build_time", "value": est, "unit": "s/iter", "n_gpus": 0,
+           "steps": len(ts), "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": False,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+           "cpu_baseline": {"value": est, "unit": "s/iter", "cores": res["cores"], "kind": "port", "sample": sample},
+           "e2e": {"value": est, "unit": "s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+def time_builds(eng, dm_dev, warmup, steps):
+    import torch
+    for _ in range(warmup):
+        eng.get_jk(dm_dev, hermi=1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.get_jk(dm_dev, hermi=1)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def extra_configs(peak_probe, dev):
+    """The other BASELINE.json configurations, 1 warm-up + 1 timed build each (1 GPU)."""
+    import torch
+    from joltqc_b200.pyscf.basis import BasisLayout
+    out = {}
+    for wl, dmk in (("benzene-ccpvtz", "ones"), ("taxol-svp", "ones"), ("valinomycin-tzvp", "decay"), ("valinomycin-tzvpp", "ones")):
+        mol, label = build_mol(wl)
+        lay = BasisLayout.from_mol(mol, alignment=4)
+        eng = lay.engine()
+        dm_dev = torch.as_tensor(make_dm(mol, dmk), device=dev)
+        eng.q_matrix(0.0)
+        ms = time_builds(eng, dm_dev, 1, 1 if mol.nao > 1500 else 3)
+        counts, pw, _ = eng.last_stats()
+        fl = total_flops(counts, pw)
+        out["%s/dm=%s" % (wl, dmk)] = {"s_per_build": ms * 1e-3, "quartets": int(counts.sum()), "tflops": fl / (ms * 1e-3) / 1e12,
+                                       "frac_of_fp64_peak": fl / (ms * 1e-3) / 1e12 / peak_probe}
+        lay._cache.clear()
+        del eng
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "jqc-kernels"])
     ap.add_argument("--workload", default="valinomycin-tzvp", choices=sorted(WORKLOADS))
     ap.add_argument("--dm", default="ones", choices=["ones", "decay"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other configs and the reference-kernel leg")
     ap.add_argument("--class-profile", default=None, help="write the per-class device-time table to this file")
     args = ap.parse_args()
 
@@ -202,42 +324,37 @@ def main():
     mol, label = build_mol(args.workload)
     lay = BasisLayout.from_mol(mol, alignment=4)
     dm = make_dm(mol, args.dm)
-    config = {"workload": label, "basis": WORKLOADS[args.workload][1], "nao": mol.nao, "nao_cart_kernel": lay.nao,
-              "shells": int((~lay.pad_id).sum()), "dm": args.dm, "hermi": 1, "with_j": True, "with_k": True,
-              "cutoff": 1e-13, "parallelism": f"static ij-tile interleave over {max(world, 1)} GPU(s) + 1 NCCL all_reduce",
-              "l2": "working set D+J+K = %.0f MB > 126 MB L2, no explicit flush" % (3 * lay.nao**2 * 8 / 1e6)}
+    config = _config(args, mol, lay, label, world)
 
     if args.impl == "reference":
-        # The reference's CPU path for get_jk is PySCF/libcint, which is not installed; the
-        # in-repo CPU restatement (oracle port) is timed instead on all host threads.
-        if rank != 0:
-            return
-        res = None
-        for _ in range(max(1, args.warmup > 0) + 0):
-            pass
-        ts = []
-        for _ in range(max(1, args.steps)):
-            res = cpu_port_baseline(lay, dm, budget_s=20.0)
-            ts.append(res["seconds_sample"])
-            if sum(ts) > 120:
-                break
-        npair = lay.nbasis * (lay.nbasis + 1) // 2
-        frac = 1.0 / res["stride"]
-        est = float(np.median(ts)) / frac
-        line = {"impl": "reference", "metric": "fp64_jk_build_time", "value": est, "unit": "s/iter", "n_gpus": 0,
-                "steps": len(ts), "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": False,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": est, "unit": "s/iter", "cores": res["cores"], "kind": "port",
-                                 "sample": f"every {res['stride']}th (ij) shell pair of the same build "
-                                           f"({res['quartets_sample']} quartets in {np.median(ts):.2f} s), extrapolated x{res['stride']}"},
-                "e2e": {"value": est, "unit": "s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        _emit(line)
+        # The reference's CPU path for get_jk is PySCF/libcint, which is not installed; the in-repo
+        # CPU restatement (oracle port) is timed instead, on all host cores (set explicitly: torchrun
+        # exports OMP_NUM_THREADS=1).  Rank 0 only.
+        if rank == 0:
+            run_reference_arm(args, lay, dm, config)
         return
 
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: joltqc_b200 has no CPU J/K path (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    if args.impl == "jqc-kernels":
+        if rank != 0:
+            return
+        eng = lay.engine()
+        dm_dev = torch.as_tensor(dm, device=dev)
+        eng.q_matrix(0.0)
+        leg = ref_kernels_leg(lay, eng, dm_dev, reps=max(1, args.steps))
+        if "unavailable" in leg:
+            _emit({"impl": "jqc-kernels", "unavailable": leg["unavailable"]})
+            return
+        _emit({"impl": "jqc-kernels", "metric": "fp64_jk_build_time", "value": leg["value"], "unit": "s/iter", "n_gpus": 1,
+               "steps": max(1, args.steps), "warmup": 1, "ms_per_step": leg["value"] * 1e3, "higher_is_better": False,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "ref_kernels": leg})
+        return
+
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -245,9 +362,9 @@ def main():
     eng = lay.engine()
     if world > 1:
         eng.enable_sharding(rank, world)
-    dev = torch.device("cuda", local_rank)
     dm_dev = torch.as_tensor(dm, device=dev)
     dm_pin = torch.as_tensor(dm).pin_memory()
+    out_pin = (torch.empty_like(dm_pin).pin_memory(), torch.empty_like(dm_pin).pin_memory())
     t0 = time.perf_counter()
     eng.q_matrix(0.0)
     torch.cuda.synchronize()
@@ -263,13 +380,16 @@ def main():
         return eng.get_jk(dm_dev, hermi=1)
 
     def step_e2e():
-        d = dm_pin.to(dev, non_blocking=True)
+        if world == 1:
+            # the host-buffer C entry point: H2D of D, the build, D2H of J and K inside jqc_get_jk_host
+            return eng.get_jk_host(dm_pin.numpy(), hermi=1, out=(out_pin[0].numpy(), out_pin[1].numpy()))
+        d = dm_pin.to(dev, non_blocking=True)           # every rank receives D from its host
         vj, vk = eng.get_jk(d, hermi=1)
         if rank == 0:
-            out = (vj.to("cpu", non_blocking=False), vk.to("cpu", non_blocking=False))
-        else:
-            out = None
-        return out
+            out_pin[0].copy_(vj, non_blocking=True)
+            out_pin[1].copy_(vk, non_blocking=True)
+        torch.cuda.synchronize()
+        return None
 
     for _ in range(args.warmup):
         step_device()
@@ -283,30 +403,39 @@ def main():
         vj, vk = step_device()
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1) / args.steps
+    ms_local = ev0.elapsed_time(ev1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    # build-only time of this rank (before the all_reduce): one extra step, timed around build_partial
+    torch.cuda.synchronize()
+    eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eb0.record()
+    eng.build_partial(dm_dev, hermi=1)
+    eb1.record()
+    barrier()
+    ms_build_local = eb0.elapsed_time(eb1)
     counts, pw, launches = eng.last_stats()
     flops_local = total_flops(counts, pw)
-    t = torch.tensor([ms, flops_local, float(counts.sum())], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_local, flops_local, float(counts.sum()), ms_build_local], dtype=torch.float64, device=dev)
+    ms = ms_local
+    per_rank = None
     if dist is not None:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, flops_all, nq_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        ms = max(float(x[0]) for x in allt)
+        flops_all = sum(float(x[1]) for x in allt)
+        nq_all = sum(float(x[2]) for x in allt)
+        per_rank = {"partial_build_ms": [round(float(x[3]), 2) for x in allt], "quartets": [int(float(x[2])) for x in allt],
+                    "step_ms": [round(float(x[0]), 2) for x in allt]}
     else:
         flops_all, nq_all = flops_local, float(counts.sum())
 
     # end to end through host buffers
     step_e2e()
     barrier()
+    n_e2e = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    n_e2e = max(1, min(args.steps, 3))
     for _ in range(n_e2e):
         step_e2e()
-    e1.record()
     barrier()
     e2e_s = (time.perf_counter() - t0) / n_e2e
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -362,21 +491,30 @@ def main():
                      "traffic": None,
                      "peak_source": "DFMA probe kernel measured in this run (%.2f TFLOP/s per GPU); nominal SMs x 128 x clock = %s TFLOP/s at the sampled %.0f MHz; MEASURED_PEAKS.json has no FP64 entry" % (peak_probe, ("%.2f" % peak_clock) if peak_clock else "n/a", sm_mhz),
                      "algorithmic_flops_per_build": flops_all, "quartets_per_build": nq_all,
-                     "kernel": "whole get_jk (Rys J/K kernels + task generation + AO transforms); per-class shares in profiles/",
+                     "kernel": "whole get_jk (Rys J/K kernels incl. in-kernel screening, AO transforms); per-class shares in profiles/",
                      "top_classes": top},
         "e2e": {"value": e2e_s, "unit": "s/iter", "h2d_bytes_per_step": int(dm_pin.numel() * 8) * max(world, 1),
-                "d2h_bytes_per_step": int(2 * dm_pin.numel() * 8)},
+                "d2h_bytes_per_step": int(2 * dm_pin.numel() * 8),
+                "path": "jqc_get_jk_host (pinned host buffers)" if world == 1 else "per-rank H2D of D + sharded build + all_reduce + D2H on rank 0"},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
         "schwarz_setup_s": t_schwarz,
         "checksum": {"sum_J": chk[0], "sum_K": chk[1]},
     }
+    if per_rank is not None:
+        line["per_rank"] = per_rank
+    if world == 1 and not args.no_extras:
+        line["ref_kernels"] = ref_kernels_leg(lay, eng, dm_dev)
+        if "value" in line["ref_kernels"]:
+            line["ref_kernels"]["speedup_of_this_engine"] = line["ref_kernels"]["value"] / (ms * 1e-3)
+        line["extra"] = extra_configs(peak_probe, dev)
     if not args.no_cpu_baseline and world == 1:
         res = cpu_port_baseline(lay, dm)
         est = res["seconds_sample"] * res["stride"]
         line["cpu_baseline"] = {"value": est, "unit": "s/iter", "cores": res["cores"], "kind": "port",
                                 "sample": f"every {res['stride']}th (ij) shell pair of the same build "
-                                          f"({res['quartets_sample']} quartets in {res['seconds_sample']:.2f} s), extrapolated x{res['stride']}"}
+                                          f"({res['quartets_sample']} quartets in {res['seconds_sample']:.2f} s), extrapolated x{res['stride']}",
+                                "anchor": cpu_anchor()}
     _emit(line)
     if dist is not None:
         dist.barrier()

@@ -161,12 +161,21 @@ class JKEngine:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         return buf
 
-    def get_jk_host(self, dm, hermi=0, with_j=True, with_k=True, omega=None, cutoff_fp64=1e-13, cutoff_fp32=1e-13):
-        """Host-buffer entry point (numpy in, numpy out): H2D + build + D2H inside the C call."""
+    def get_jk_host(self, dm, hermi=0, with_j=True, with_k=True, omega=None, cutoff_fp64=1e-13, cutoff_fp32=1e-13,
+                    out=None):
+        """Host-buffer entry point (numpy in, numpy out): H2D + build + D2H inside the C call
+        (jqc_get_jk_host).  ``out=(vj, vk)``: preallocated C-contiguous float64 arrays shaped like
+        ``dm`` (e.g. views of pinned memory) that receive the results."""
         d = np.ascontiguousarray(dm, dtype=np.float64)
         d3 = d.reshape(-1, d.shape[-2], d.shape[-1])
-        vj = np.empty_like(d3) if with_j else None
-        vk = np.empty_like(d3) if with_k else None
+        if out is not None:
+            vj, vk = (o.reshape(d3.shape) if o is not None else None for o in out)
+            for o, w in ((vj, with_j), (vk, with_k)):
+                if w and (o is None or o.dtype != np.float64 or not o.flags.c_contiguous):
+                    raise ValueError("out buffers must be C-contiguous float64 arrays shaped like dm")
+        else:
+            vj = np.empty_like(d3) if with_j else None
+            vk = np.empty_like(d3) if with_k else None
         _lib.check(self.L.jqc_get_jk_host(self.h, d3.ctypes.data, d3.shape[0], int(hermi), int(with_j), int(with_k),
                                           0.0 if omega is None else float(omega), float(cutoff_fp64), float(cutoff_fp32),
                                           vj.ctypes.data if with_j else None, vk.ctypes.data if with_k else None))

@@ -24,10 +24,6 @@ __all__ = ["generate_jk_kernel", "generate_get_j", "generate_get_k", "generate_g
 PAIR_CUTOFF = 1e-13  # jk.py:48 — applied inside the engine (tile lists)
 
 
-def _asarray_like(x):
-    return x
-
-
 def generate_jk_kernel(basis_layout: BasisLayout, cutoff_fp64=1e-13, cutoff_fp32=1e-13):
     assert basis_layout.alignment % TILE == 0, "the J/K layout must be padded to TILE (jqc/pyscf/__init__.py:189)"
     engine = basis_layout.engine()
@@ -77,28 +73,24 @@ def generate_get_jk(basis_layout, cutoff_fp64=1e-13, cutoff_fp32=1e-13):
     return generate_jk_kernel(basis_layout, cutoff_fp64=cutoff_fp64, cutoff_fp32=cutoff_fp32)
 
 
-def _to_dev(engine_like, a):
-    import torch
-    return a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
-
-
 def generate_get_veff():
-    """RHF ``get_veff`` with the incremental (delta-density) Fock build of jk.py:78-90."""
+    """RHF ``get_veff`` with the incremental (delta-density) Fock build of jk.py:78-90.  Works in the
+    array namespace of ``dm`` (CuPy with GPU4PySCF, torch, or numpy -> torch), like the reference,
+    so that a CuPy density goes straight to ``get_jk`` and a CuPy potential comes back."""
+    from .rks import _asarray_like, _xp
 
     def get_veff(mf, mol=None, dm=None, dm_last=None, vhf_last=None, hermi=1):
-        import torch
         if dm is None:
             dm = mf.make_rdm1()
-        dev = None
-        dm_t = dm if isinstance(dm, torch.Tensor) else torch.as_tensor(np.asarray(dm))
-        if dm_last is not None and mf.direct_scf:
-            last = dm_last if isinstance(dm_last, torch.Tensor) else torch.as_tensor(np.asarray(dm_last))
-            dm_t = dm_t - last.to(dm_t.device)
-        vj, vk = mf.get_jk(mol, dm_t, hermi)
+        if _xp(dm) is np:
+            import torch
+            dm = torch.as_tensor(np.asarray(dm))
+        if dm_last is not None and not isinstance(dm_last, (int, float)) and mf.direct_scf:
+            dm = dm - _asarray_like(dm, dm_last)
+        vj, vk = mf.get_jk(mol, dm, hermi)
         vhf = vj - 0.5 * vk
-        if vhf_last is not None:
-            last = vhf_last if isinstance(vhf_last, torch.Tensor) else torch.as_tensor(np.asarray(vhf_last))
-            vhf = vhf + last.to(vhf.device)
+        if vhf_last is not None and not isinstance(vhf_last, (int, float)):
+            vhf = vhf + _asarray_like(vhf, vhf_last)
         return vhf
 
     return get_veff

@@ -78,8 +78,17 @@ def lib():
                                       ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_float, dp, dp,
                                       ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_long)]
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         _LIB = L
     return _LIB
+
+
+def use_all_cores():
+    """Pin the OpenMP thread count to the cores this process may run on (torchrun sets
+    OMP_NUM_THREADS=1, which silently made the CPU baseline single-threaded in round 1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_num_threads(n)
+    return lib().oracle_num_threads()
 
 
 def _p(a, t):
