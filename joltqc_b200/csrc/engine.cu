@@ -112,6 +112,7 @@ struct jqc_engine {
     // brick kernel (jk_brick.cuh) for the classes of <= 108 integrals and one density matrix;
     // JQC_BRICK=0 falls back to the quartet-list kernels (kept as the cross-check of the tests)
     int use_brick = 1;
+    int use_bwarp = 1;          // brick-scheduled multi-lane kernel (jk_bwarp.cuh) for the larger classes
     int brick_ichunk = 8;
     // chunking of the quartet-list path; JQC_QUEUE_CAP / JQC_KL_CHUNK shrink them so that small test
     // molecules exercise the multi-chunk loops
@@ -119,9 +120,9 @@ struct jqc_engine {
     int kl_chunk_max = 2048;
     // brick launches need no queue: they go round-robin to auxiliary streams so that the tail of one
     // launch overlaps the start of the next (and the quartet-list launches of the main stream)
-    static constexpr int NAUX = 2;
-    cudaStream_t aux[NAUX] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr};
+    static constexpr int NAUX = 3;
+    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr};
     int use_aux = 1;
     // state of the last build
     int last_n = 0, last_neff = 0, last_hermi = 1, last_j = 0, last_k = 0, launches = 0;
@@ -151,6 +152,7 @@ extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine
     e->device = device;
     if (const char* m = getenv("JQC_SMALL_TILES")) e->small_tiles = atoi(m) != 0;
     if (const char* m = getenv("JQC_BRICK")) e->use_brick = atoi(m) != 0;
+    if (const char* m = getenv("JQC_BWARP")) e->use_bwarp = atoi(m) != 0;
     if (const char* m = getenv("JQC_BRICK_ICHUNK")) e->brick_ichunk = std::max(1, atoi(m));
     if (const char* m = getenv("JQC_AUX_STREAMS")) e->use_aux = atoi(m) != 0;
     if (const char* m = getenv("JQC_QUEUE_CAP")) e->queue_cap = std::min<size_t>(QUEUE_CAP, std::max<size_t>(256, (size_t)atoll(m)));
@@ -537,7 +539,8 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
         const int li = e->gl[gi], lj = e->gl[gj], lk = e->gl[gk], ll = e->gl[gl];
         const int key = ((li * 5 + lj) * 5 + lk) * 5 + ll;
         const long long pw = (long long)e->gnp[gi] * e->gnp[gj] * e->gnp[gk] * e->gnp[gl];
-        if (e->use_brick && neff == 1 && !e->small_tiles && brick_shape(li, lj, lk, ll).fits) {
+        const bool brick_small = brick_shape(li, lj, lk, ll).fits;
+        if (e->use_brick && neff == 1 && !e->small_tiles && (brick_small || (e->use_bwarp && jk_bwarp_supported(li, lj, lk, ll)))) {
             const int n_kl_pairs = qd->h_pair_off[pkl + 1] - qd->h_pair_off[pkl];
             const int n_ij_pairs = qd->h_pair_off[pij + 1] - qd->h_pair_off[pij];
             if (n_kl_pairs == 0 || n_ij_pairs == 0) continue;
@@ -558,15 +561,9 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             b.j_idx = qd->j_idx.p; b.j_q = qd->j_q.p; b.j_tq = qd->j_tq.p;
             b.qmax_ij = qd->h_qmax[pij];
             b.tri = gi == gk;
-            b.n_blk = (n_kl_pairs + 31) / 32;
-            // bra chunk: 8 shells per task, fewer when the launch would not fill the GPU otherwise
-            {
-                const long long want = 4LL * e->nsm * 16 * e->world;
-                int ic = e->brick_ichunk;
-                while (ic > 1 && (long long)b.n_blk * ((b.i_count + ic - 1) / ic) < want) ic >>= 1;
-                b.ichunk = ic;
-            }
-            b.n_ichunk = (b.i_count + b.ichunk - 1) / b.ichunk;
+            b.n_ij = n_ij_pairs;
+            b.ichunk_req = e->brick_ichunk;
+            b.n_blk = b.ichunk = b.n_ichunk = b.jsplit = 0;      // set by the launcher (brick_decompose)
             b.rank = e->rank; b.world = e->world;
             b.work = e->d_counters.p + cid;
             b.qcount = e->d_qcounts.p + cid;
@@ -576,7 +573,8 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
                 e0 = e->ev[nev++]; e1 = e->ev[nev++];
                 CU(cudaEventRecord(e0, st));
             }
-            CU(jk_brick_launch(li, lj, lk, ll, variant, b, e->nsm, fork ? e->aux[n_brick++ % jqc_engine::NAUX] : st));
+            CU(jk_brick_launch(li, lj, lk, ll, variant | (brick_small ? 0 : 8), b, e->nsm,
+                               fork ? e->aux[n_brick++ % jqc_engine::NAUX] : st));
             if (e->profiling) CU(cudaEventRecord(e1, st));
             e->launches += 1;
             e->chunks.push_back({key, pw});

@@ -48,11 +48,36 @@ struct BrickArgs {
     const float* __restrict__ j_tq;
     float qmax_ij;                            // largest q of the bra group pair
     int tri;                                  // gi == gk: k <= i and (k,l) <= (i,j) must be tested per lane
-    int ichunk, n_ichunk, n_blk;              // task = (ket block of 32 pairs) x (chunk of bra shells)
+    int ichunk, n_ichunk, n_blk;              // task = (ket block of 32 pairs) x (chunk of bra shells) x (slice of the j lists)
+    int jsplit;                               // slices per j list (> 1 only when a launch has too few tasks to fill the GPU)
+    int n_ij, ichunk_req;                     // bra pairs in the lists and the requested bra chunk (the launcher decomposes)
     int rank, world;                          // this GPU takes tasks rank, rank + world, ...
     unsigned* __restrict__ work;              // dynamic task counter (zeroed per build)
     unsigned long long* __restrict__ qcount;  // evaluated quartets (accounting)
 };
+
+// Task decomposition of a launch: `per_task` ket pairs per warp task (32 for the one-lane-per-quartet
+// kernel, 32/T for the multi-lane kernel); bra chunks of ichunk_req shells, fewer when the launch
+// would not fill the GPU, and for small molecules the j lists are sliced as well so that one
+// warp's serial chain stays short.
+inline void brick_decompose(BrickArgs& b, int per_task, int nsm)
+{
+    b.n_blk = (b.n_kl + per_task - 1) / per_task;
+    const long long want = 4LL * nsm * 16 * b.world;
+    int ic = b.ichunk_req < 1 ? 1 : b.ichunk_req;
+    while (ic > 1 && (long long)b.n_blk * ((b.i_count + ic - 1) / ic) < want) ic >>= 1;
+    b.ichunk = ic;
+    b.n_ichunk = (b.i_count + ic - 1) / ic;
+    b.jsplit = 1;
+    const long long have = (long long)b.n_blk * b.n_ichunk;
+    const int jmax = b.n_ij / (b.i_count > 0 ? b.i_count : 1) / 2;           // >= 2 partners per slice on average
+    if (have < want / 2 && jmax > 1) {
+        long long js = (want / 2 + have - 1) / have;
+        if (js > 16) js = 16;
+        if (js > jmax) js = jmax;
+        b.jsplit = (int)(js < 1 ? 1 : js);
+    }
+}
 
 // Primitive-pair data of the bra pair (i,j) of a step, staged in shared memory once per warp
 // (the pair is the same for all 32 lanes): 8 doubles per primitive pair.  Lane p < npi*npj
@@ -230,7 +255,7 @@ jk_brick_kernel(const BrickArgs a)
     const float log_max = ordered_to_float(*a.log_max_ordered);
     const float dmaxf = fmaxf(log_max, -36.8f);
     const double paircut = log(1e-13) - (double)log_max;       // jk.py:185-187, 412
-    const unsigned ntask = (unsigned)a.n_blk * (unsigned)a.n_ichunk;
+    const unsigned ntask = (unsigned)a.n_blk * (unsigned)a.n_ichunk * (unsigned)a.jsplit;
     // shared memory: [Rys table of this class][lane-private slots: element-major, lane-minor]
     const double2* __restrict__ s_rys = brick_smem;
     rys_table_to_smem<S::NROOTS>(brick_smem);
@@ -247,6 +272,8 @@ jk_brick_kernel(const BrickArgs a)
         if (lane == 0) t = atomicAdd(a.work, 1u);
         t = __shfl_sync(FULL, t, 0) * (unsigned)a.world + (unsigned)a.rank;
         if (t >= ntask) break;
+        const int js = (int)(t % (unsigned)a.jsplit);
+        t /= (unsigned)a.jsplit;
         const int blk = (int)(t % (unsigned)a.n_blk), ic = (int)(t / (unsigned)a.n_blk);
         const int p = blk * 32 + lane;
         const bool pvalid = p < a.n_kl;
@@ -290,8 +317,13 @@ jk_brick_kernel(const BrickArgs a)
         for (int ish = i_lo; ish < i_hi; ish++) {
             if (a.tri && ish < kmin) continue;
             int e = a.j_off[ish - a.i_first];
-            const int e_end = a.j_off[ish - a.i_first + 1];
-            if (e == e_end) continue;
+            int e_end = a.j_off[ish - a.i_first + 1];
+            if (a.jsplit > 1) {
+                const int len = (e_end - e + a.jsplit - 1) / a.jsplit;
+                e += js * len;
+                e_end = min(e_end, e + len);
+            }
+            if (e >= e_end) continue;
             if (!(a.j_q[e] + Qb + dmaxf > a.cutoff)) continue;
             const double* __restrict__ bi = a.basis + ish * BASIS_STRIDE;
             const double4 ri = *reinterpret_cast<const double4*>(bi);

@@ -6,7 +6,7 @@
 
 #include "jk_tile16.cuh"
 #include "jk_warp.cuh"
-#include "jk_brick.cuh"
+#include "jk_bwarp.cuh"
 #include "jk_launch.h"
 
 namespace jqc {
@@ -70,7 +70,31 @@ static cudaError_t launch_warp(const JKArgs& a, int nsm, cudaStream_t st)
 }
 
 template <int LK, int LL, bool DO_J, bool DO_K>
-static cudaError_t launch_brick(const BrickArgs& a, int nsm, cudaStream_t st)
+static cudaError_t launch_bwarp(const BrickArgs& a_in, int nsm, cudaStream_t st)
+{
+    using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
+    using P = BWarpPlan<JQC_LI, JQC_LJ, LK, LL>;
+    if constexpr (S::N > JQC_SMALL_N && P::FITS && JQC_LI <= 3) {
+        auto kern = jk_bwarp_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, P::NWARPS>;
+        static std::atomic<int> cache[JQC_MAX_DEVICES];
+        int blocks_per_sm = 1;
+        cudaError_t e = blocks_per_sm_cached(cache, kern, P::NWARPS * 32, P::SMEM, &blocks_per_sm);
+        if (e != cudaSuccess) return e;
+        BrickArgs b = a_in;
+        brick_decompose(b, P::QPW, nsm);
+        const long long ntask = ((long long)b.n_blk * b.n_ichunk * b.jsplit + b.world - 1) / b.world;
+        long long blocks = (ntask + P::NWARPS - 1) / P::NWARPS;
+        if (blocks > (long long)nsm * blocks_per_sm) blocks = (long long)nsm * blocks_per_sm;
+        if (blocks < 1) blocks = 1;
+        kern<<<(unsigned)blocks, P::NWARPS * 32, P::SMEM, st>>>(b);
+        return cudaGetLastError();
+    } else {
+        return cudaErrorInvalidValue;
+    }
+}
+
+template <int LK, int LL, bool DO_J, bool DO_K>
+static cudaError_t launch_brick(const BrickArgs& a_in, int nsm, cudaStream_t st)
 {
     using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
     using P = BrickPlan<JQC_LI, JQC_LJ, LK, LL>;
@@ -80,8 +104,11 @@ static cudaError_t launch_brick(const BrickArgs& a, int nsm, cudaStream_t st)
         int blocks_per_sm = 1;
         cudaError_t e = blocks_per_sm_cached(cache, kern, P::NWARPS * 32, P::SMEM, &blocks_per_sm);
         if (e != cudaSuccess) return e;
+        BrickArgs b = a_in;
+        brick_decompose(b, 32, nsm);
+        const BrickArgs& a = b;
         // no more warps than tasks
-        const long long ntask = ((long long)a.n_blk * a.n_ichunk + a.world - 1) / a.world;
+        const long long ntask = ((long long)a.n_blk * a.n_ichunk * a.jsplit + a.world - 1) / a.world;
         long long blocks = (ntask + P::NWARPS - 1) / P::NWARPS;
         if (blocks > (long long)nsm * blocks_per_sm) blocks = (long long)nsm * blocks_per_sm;
         if (blocks < 1) blocks = 1;
@@ -164,6 +191,9 @@ static cudaError_t brick_variant(int variant, const BrickArgs& a, int nsm, cudaS
         case 3: return launch_brick<LK, LL, true, true>(a, nsm, st);
         case 1: return launch_brick<LK, LL, true, false>(a, nsm, st);
         case 2: return launch_brick<LK, LL, false, true>(a, nsm, st);
+        case 11: return launch_bwarp<LK, LL, true, true>(a, nsm, st);
+        case 9: return launch_bwarp<LK, LL, true, false>(a, nsm, st);
+        case 10: return launch_bwarp<LK, LL, false, true>(a, nsm, st);
     }
     return cudaErrorInvalidValue;
 }

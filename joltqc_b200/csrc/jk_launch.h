@@ -38,7 +38,13 @@ inline cudaError_t jk_launch(int li, int lj, int lk, int ll, int variant, const 
     return cudaErrorInvalidValue;
 }
 
-// Classes that run on the brick kernel: brick_shape(li, lj, lk, ll).fits (jk_brick.cuh).
+// Classes that run on the one-lane brick kernel: brick_shape(li, lj, lk, ll).fits (jk_brick.cuh);
+// the brick-scheduled multi-lane kernel (jk_bwarp.cuh, variant bit 3) takes the larger classes up to f shells.
+inline bool jk_bwarp_supported(int li, int lj, int lk, int ll)
+{
+    auto nf = [](int l) { return (l + 1) * (l + 2) / 2; };
+    return li <= 3 && nf(li) * nf(lj) * nf(lk) * nf(ll) > JQC_SMALL_N_VALUE;
+}
 
 inline cudaError_t jk_brick_launch(int li, int lj, int lk, int ll, int variant, const BrickArgs& a, int nsm, cudaStream_t st)
 {

@@ -297,7 +297,8 @@ def test_multi_chunk_task_queues(torch_cuda, monkeypatch, brick):
     _, _, launches0 = lay0.engine().last_stats()
     lay = _fresh_check(monkeypatch, {"JQC_QUEUE_CAP": 4096, "JQC_KL_CHUNK": 5}, benzene(), "cc-pvtz", scale=1.0 / 264)
     _, _, launches = lay.engine().last_stats()
-    assert launches > 3 * launches0, (launches, launches0)     # many more chunks were really launched
+    if brick == 0:     # (with the brick kernels on, no class of this molecule uses the queue any more)
+        assert launches > 3 * launches0, (launches, launches0)     # many more chunks were really launched
 
 
 @pytest.mark.parametrize("ichunk", [1, 3, 64])
