@@ -152,7 +152,7 @@ extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine
     e->device = device;
     if (const char* m = getenv("JQC_SMALL_TILES")) e->small_tiles = atoi(m) != 0;
     if (const char* m = getenv("JQC_BRICK")) e->use_brick = atoi(m) != 0;
-    if (const char* m = getenv("JQC_BWARP")) e->use_bwarp = atoi(m) != 0;
+    if (const char* m = getenv("JQC_BWARP")) e->use_bwarp = atoi(m);   // 0 off, 1 measured table, 2 every supported class
     if (const char* m = getenv("JQC_BRICK_ICHUNK")) e->brick_ichunk = std::max(1, atoi(m));
     if (const char* m = getenv("JQC_AUX_STREAMS")) e->use_aux = atoi(m) != 0;
     if (const char* m = getenv("JQC_QUEUE_CAP")) e->queue_cap = std::min<size_t>(QUEUE_CAP, std::max<size_t>(256, (size_t)atoll(m)));
@@ -540,7 +540,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
         const int key = ((li * 5 + lj) * 5 + lk) * 5 + ll;
         const long long pw = (long long)e->gnp[gi] * e->gnp[gj] * e->gnp[gk] * e->gnp[gl];
         const bool brick_small = brick_shape(li, lj, lk, ll).fits;
-        if (e->use_brick && neff == 1 && !e->small_tiles && (brick_small || (e->use_bwarp && jk_bwarp_supported(li, lj, lk, ll)))) {
+        if (e->use_brick && neff == 1 && !e->small_tiles && (brick_small || (e->use_bwarp && jk_bwarp_supported(li, lj, lk, ll, e->use_bwarp)))) {
             const int n_kl_pairs = qd->h_pair_off[pkl + 1] - qd->h_pair_off[pkl];
             const int n_ij_pairs = qd->h_pair_off[pij + 1] - qd->h_pair_off[pij];
             if (n_kl_pairs == 0 || n_ij_pairs == 0) continue;

@@ -40,10 +40,14 @@ inline cudaError_t jk_launch(int li, int lj, int lk, int ll, int variant, const 
 
 // Classes that run on the one-lane brick kernel: brick_shape(li, lj, lk, ll).fits (jk_brick.cuh);
 // the brick-scheduled multi-lane kernel (jk_bwarp.cuh, variant bit 3) takes the larger classes up to f shells.
-inline bool jk_bwarp_supported(int li, int lj, int lk, int ll)
+// Which of those classes actually use it is a measured table (jk_class_select.h, tools/gen_class_select.py);
+// mode 2 (JQC_BWARP=2) forces it for every supported class.
+#include "jk_class_select.h"
+inline bool jk_bwarp_supported(int li, int lj, int lk, int ll, int mode = 1)
 {
     auto nf = [](int l) { return (l + 1) * (l + 2) / 2; };
-    return li <= 3 && nf(li) * nf(lj) * nf(lk) * nf(ll) > JQC_SMALL_N_VALUE;
+    if (!(li <= 3 && nf(li) * nf(lj) * nf(lk) * nf(ll) > JQC_SMALL_N_VALUE)) return false;
+    return mode >= 2 || jk_class_prefers_bwarp(li, lj, lk, ll);
 }
 
 inline cudaError_t jk_brick_launch(int li, int lj, int lk, int ll, int variant, const BrickArgs& a, int nsm, cudaStream_t st)

@@ -324,3 +324,16 @@ def test_brick_density_screening_counts(torch_cuda):
         orc = _oracle(lay)
         orc.get_jk(dm, 1, with_j, with_k, None, 1e-9)
         assert np.array_equal(counts, orc.last_counts), (with_j, with_k)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_multilane_kernel_variants(torch_cuda, monkeypatch, mode):
+    """JQC_BWARP=0: every large class on the quartet-list multi-lane kernel (jk_warp.cuh);
+    JQC_BWARP=2: every large class on the brick-scheduled one (jk_bwarp.cuh).  The default (1)
+    mixes them by a measured table, so both have to agree with the oracle on their own."""
+    lay = _fresh_check(monkeypatch, {"JQC_BWARP": mode}, benzene(), "cc-pvtz", scale=1.0 / 264)
+    counts, _, _ = lay.engine().last_stats()
+    orc = _oracle(lay)
+    orc.get_jk(random_dm(lay._mol.nao, 9) / 264, 1)
+    assert np.array_equal(counts, orc.last_counts)
+    _fresh_check(monkeypatch, {"JQC_BWARP": mode}, H2O, "def2-tzvpp", omega=0.3)
