@@ -81,6 +81,9 @@ struct QData {                    // per-omega Schwarz data
     std::vector<int> h_pair_off;  // npairs + 1: segment of each group pair in kl / j_idx
     std::vector<int> h_joff_off;  // npairs: start of each group pair's row offsets in j_off
     std::vector<float> h_qmax;    // npairs: largest q of the group pair
+    // primitive-pair tables in ket-list and bra-list order (pair_prim_kernel), 8 doubles per primitive pair
+    DevBuf<double> ket_tab, bra_tab;
+    std::vector<size_t> h_tab_off;   // npairs: offset (doubles) of each group pair's segment in both tables
 };
 
 struct ChunkRec { int key; long long pw; };   // class key and primitive weight of a launch
@@ -353,6 +356,7 @@ static int get_qdata(jqc_engine* e, double omega, QData** out)
         std::vector<ushort2> kl;
         std::vector<float> kl_q, kl_tq, j_q, j_tq;
         std::vector<unsigned short> j_idx;
+        std::vector<ushort2> j_pairs;      // (a, b) in bra-list order, for the primitive-pair table
         std::vector<int> j_off;
         qd->h_pair_off.assign(1, 0);
         struct Ent { int bucket; float q; unsigned short a, b; };
@@ -377,6 +381,7 @@ static int get_qdata(jqc_engine* e, double omega, QData** out)
                     std::sort(row.begin(), row.end(), [](const Ent& x, const Ent& y) { return x.q != y.q ? x.q > y.q : x.b < y.b; });
                     for (auto& r : row) {
                         j_idx.push_back(r.b);
+                        j_pairs.push_back(make_ushort2(r.a, r.b));
                         j_q.push_back(r.q);
                         j_tq.push_back(h_tq[(size_t)(r.a / JQC_TILE) * nt + r.b / JQC_TILE]);
                     }
@@ -402,6 +407,30 @@ static int get_qdata(jqc_engine* e, double omega, QData** out)
         CU(qd->j_q.upload(j_q));
         CU(qd->j_tq.upload(j_tq));
         CU(qd->j_off.upload(j_off));
+        // primitive-pair tables of both lists
+        DevBuf<ushort2> d_jpairs;
+        CU(d_jpairs.upload(j_pairs));
+        size_t tot = 0;
+        for (int ga = 0, P = 0; ga < e->ngroups; ga++)
+            for (int gb = 0; gb <= ga; gb++, P++) {
+                qd->h_tab_off.push_back(tot);
+                tot += (size_t)(qd->h_pair_off[P + 1] - qd->h_pair_off[P]) * e->gnp[ga] * e->gnp[gb] * 8;
+            }
+        CU(qd->ket_tab.ensure(std::max<size_t>(tot, 1)));
+        CU(qd->bra_tab.ensure(std::max<size_t>(tot, 1)));
+        for (int ga = 0, P = 0; ga < e->ngroups; ga++)
+            for (int gb = 0; gb <= ga; gb++, P++) {
+                const int n = qd->h_pair_off[P + 1] - qd->h_pair_off[P];
+                if (n == 0) continue;
+                const long long work = (long long)n * e->gnp[ga] * e->gnp[gb];
+                const unsigned blocks = (unsigned)((work + 255) / 256);
+                pair_prim_kernel<<<blocks, 256>>>(e->d_basis.p, qd->kl.p + qd->h_pair_off[P], n, e->gnp[ga], e->gnp[gb],
+                                                 qd->ket_tab.p + qd->h_tab_off[P]);
+                pair_prim_kernel<<<blocks, 256>>>(e->d_basis.p, d_jpairs.p + qd->h_pair_off[P], n, e->gnp[ga], e->gnp[gb],
+                                                 qd->bra_tab.p + qd->h_tab_off[P]);
+            }
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
     }
     *out = qd.get();
     e->qcache[omega] = std::move(qd);
@@ -559,6 +588,9 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             b.i_count = e->goff[gi + 1] - e->goff[gi];
             b.j_off = qd->j_off.p + qd->h_joff_off[pij];
             b.j_idx = qd->j_idx.p; b.j_q = qd->j_q.p; b.j_tq = qd->j_tq.p;
+            b.j_base = qd->h_pair_off[pij];
+            b.bra_tab = qd->bra_tab.p + qd->h_tab_off[pij];
+            b.ket_tab = qd->ket_tab.p + qd->h_tab_off[pkl];
             b.qmax_ij = qd->h_qmax[pij];
             b.tri = gi == gk;
             b.n_ij = n_ij_pairs;

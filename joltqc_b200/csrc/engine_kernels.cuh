@@ -211,6 +211,40 @@ __global__ void __launch_bounds__(256) screen_tasks_kernel(const ScreenArgs s)
     }
 }
 
+// ------------------------------------------------------------------ primitive-pair tables
+// Static (geometry-only) data of every shell pair of a list, 8 doubles per primitive pair
+// (first * n_second + second):  [a = a1 + a2, 1/a, a2/a, c1 c2 exp(-a1 a2/a |R12|^2), Px, Py, Pz, 0]
+// with P = R1 + (a2/a)(R2 - R1).  The brick kernels read these instead of re-evaluating an exp and
+// a division per primitive pair for every quartet (the reference recomputes them per quartet,
+// 1q1t.cu:173-232; its pair algorithm stages the same quantities per block, pair_vj.cu:139-220).
+__global__ void pair_prim_kernel(const double* __restrict__ basis, const ushort2* __restrict__ pairs, int n, int np1,
+                                 int np2, double* __restrict__ out)
+{
+    const int npp = np1 * np2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * npp) return;
+    const int e = (int)(idx / npp), pp = (int)(idx - (long long)e * npp);
+    const int p1 = pp / np2, p2 = pp - p1 * np2;
+    const ushort2 sh = pairs[e];
+    const double* __restrict__ b1 = basis + sh.x * BASIS_STRIDE;
+    const double* __restrict__ b2 = basis + sh.y * BASIS_STRIDE;
+    const double dx = b2[0] - b1[0], dy = b2[1] - b1[1], dz = b2[2] - b1[2];
+    const double rr = dx * dx + dy * dy + dz * dz;
+    const double c1 = b1[4 + 2 * p1], a1 = b1[5 + 2 * p1], c2 = b2[4 + 2 * p2], a2 = b2[5 + 2 * p2];
+    const double a = a1 + a2;
+    const double inv_a = 1.0 / a;
+    const double a2_a = a2 * inv_a;
+    double* __restrict__ o = out + idx * 8;
+    o[0] = a;
+    o[1] = inv_a;
+    o[2] = a2_a;
+    o[3] = c1 * c2 * exp(-a1 * a2_a * rr);
+    o[4] = fma(dx, a2_a, b1[0]);
+    o[5] = fma(dy, a2_a, b1[1]);
+    o[6] = fma(dz, a2_a, b1[2]);
+    o[7] = 0.0;
+}
+
 // ------------------------------------------------------------------ AO transforms
 struct XformTab {
     const double* __restrict__ c2s;   // concatenated (ncart x nmol) matrices, identity when the molecule is cartesian

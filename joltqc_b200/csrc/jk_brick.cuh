@@ -51,6 +51,10 @@ struct BrickArgs {
     int ichunk, n_ichunk, n_blk;              // task = (ket block of 32 pairs) x (chunk of bra shells) x (slice of the j lists)
     int jsplit;                               // slices per j list (> 1 only when a launch has too few tasks to fill the GPU)
     int n_ij, ichunk_req;                     // bra pairs in the lists and the requested bra chunk (the launcher decomposes)
+    // primitive-pair tables (engine_kernels.cuh: pair_prim_kernel), 8 doubles per primitive pair
+    const double* __restrict__ bra_tab;       // entry of j-list element e at (e - j_base) * npi * npj * 8
+    const double* __restrict__ ket_tab;       // entry of ket pair p at p * npk * npl * 8
+    int j_base;
     int rank, world;                          // this GPU takes tasks rank, rank + world, ...
     unsigned* __restrict__ work;              // dynamic task counter (zeroed per build)
     unsigned long long* __restrict__ qcount;  // evaluated quartets (accounting)
@@ -79,69 +83,30 @@ inline void brick_decompose(BrickArgs& b, int per_task, int nsm)
     }
 }
 
-// Primitive-pair data of the bra pair (i,j) of a step, staged in shared memory once per warp
-// (the pair is the same for all 32 lanes): 8 doubles per primitive pair.  Lane p < npi*npj
-// evaluates pair p (one exp + one division each, in parallel) instead of every lane repeating
-// all of them inside its primitive loops.
-constexpr int BRA_PRIM_DOUBLES = NPRIM_MAX * NPRIM_MAX * 8;
-
-__device__ __forceinline__ void stage_bra_prims(double* __restrict__ s_bra, const double* __restrict__ bi,
-                                                const double* __restrict__ bj, const double4 ri, const double4 rj,
-                                                const int npi, const int npj, const int lane)
-{
-    __syncwarp();                                   // readers of the previous step are done
-    if (lane < npi * npj) {
-        const int ip = lane / npj, jp = lane - ip * npj;
-        const double2 cei = *reinterpret_cast<const double2*>(bi + 4 + 2 * ip);
-        const double2 cej = *reinterpret_cast<const double2*>(bj + 4 + 2 * jp);
-        const double dx = rj.x - ri.x, dy = rj.y - ri.y, dz = rj.z - ri.z;
-        const double rr_ij = dx * dx + dy * dy + dz * dz;
-        const double aij = cei.y + cej.y;
-        const double inv_aij = 1.0 / aij;
-        const double aj_aij = cej.y * inv_aij;
-        double* o = s_bra + lane * 8;
-        o[0] = aij;
-        o[1] = inv_aij;
-        o[2] = aj_aij;
-        o[3] = cei.x * cej.x * exp(-cei.y * aj_aij * rr_ij);
-        o[4] = fma(dx, aj_aij, ri.x);
-        o[5] = fma(dy, aj_aij, ri.y);
-        o[6] = fma(dz, aj_aij, ri.z);
-    }
-    __syncwarp();
-}
-
 // One shell quartet, all in registers: eri[N] += contracted integrals (reference: 1q1t.cu:86-405).
 template <int LI, int LJ, int LK, int LL>
-__device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const double* __restrict__ s_bra,
-                                               const double* __restrict__ bk, const double* __restrict__ bl,
-                                               const double4 ri, const double4 rj, const double4 rk, const double4 rl,
-                                               const int npij, const int npk, const int npl, const double omega,
-                                               const double fac, const double2* __restrict__ s_rys)
+__device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const double* __restrict__ bra,
+                                               const double* __restrict__ ket, const double4 ri, const double4 rj,
+                                               const double4 rk, const double4 rl, const int npij, const int npkl,
+                                               const double omega, const double fac, const double2* __restrict__ s_rys)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
     constexpr int NROOTS = S::NROOTS, GS = S::GSIZE, DJ = S::DJ, DK = S::DK, DL = S::DL;
     const double rjri[3] = {rj.x - ri.x, rj.y - ri.y, rj.z - ri.z};
     const double rlrk[3] = {rl.x - rk.x, rl.y - rk.y, rl.z - rk.z};
-    const double rr_kl = rlrk[0] * rlrk[0] + rlrk[1] * rlrk[1] + rlrk[2] * rlrk[2];
 #pragma unroll
     for (int n = 0; n < N; n++) eri[n] = 0.0;
 #pragma unroll 1
-    for (int kp = 0; kp < npk; kp++)
-#pragma unroll 1
-    for (int lp = 0; lp < npl; lp++) {
-        const double2 cek = *reinterpret_cast<const double2*>(bk + 4 + 2 * kp);
-        const double2 cel = *reinterpret_cast<const double2*>(bl + 4 + 2 * lp);
-        const double akl = cek.y + cel.y;
-        const double inv_akl = 1.0 / akl;
-        const double al_akl = cel.y * inv_akl;
-        const double ckcl = cek.x * cel.x * exp(-cek.y * al_akl * rr_kl);
-        const double qx = fma(rlrk[0], al_akl, rk.x), qy = fma(rlrk[1], al_akl, rk.y), qz = fma(rlrk[2], al_akl, rk.z);
+    for (int klp = 0; klp < npkl; klp++) {
+        const double4 k0 = *reinterpret_cast<const double4*>(ket + klp * 8);
+        const double4 k1 = *reinterpret_cast<const double4*>(ket + klp * 8 + 4);
+        const double akl = k0.x, inv_akl = k0.y, al_akl = k0.z, ckcl = k0.w;
+        const double qx = k1.x, qy = k1.y, qz = k1.z;
 #pragma unroll 1
         for (int ipj = 0; ipj < npij; ipj++) {
-            const double4 b0 = *reinterpret_cast<const double4*>(s_bra + ipj * 8);
-            const double4 b1 = *reinterpret_cast<const double4*>(s_bra + ipj * 8 + 4);
+            const double4 b0 = *reinterpret_cast<const double4*>(bra + ipj * 8);
+            const double4 b1 = *reinterpret_cast<const double4*>(bra + ipj * 8 + 4);
             const double aij = b0.x, inv_aij = b0.y, aj_aij = b0.z;
             const double cicj = fac * b0.w;
             const double Rpq[3] = {b1.x - qx, b1.y - qy, b1.z - qz};
@@ -224,7 +189,7 @@ __host__ __device__ constexpr BrickShape brick_shape(int li, int lj, int lk, int
     b.regs = live <= 12 ? 128 : (live <= 36 ? 168 : 255);
     b.minb = 65536 / (b.regs * b.nwarps * 32);
     b.rys_bytes = (size_t)b.nroots * (14 + 2 * b.nroots) * (RYS_NCOEF + 1) * 16;
-    b.smem = b.rys_bytes + (size_t)b.nwarps * (BRA_PRIM_DOUBLES + 32 * b.slots) * sizeof(double);
+    b.smem = b.rys_bytes + (size_t)b.nwarps * 32 * b.slots * sizeof(double);
     b.fits = b.n <= JQC_SMALL_N && b.smem * b.minb <= 216 * 1024;
     return b;
 }
@@ -259,10 +224,9 @@ jk_brick_kernel(const BrickArgs a)
     // shared memory: [Rys table of this class][lane-private slots: element-major, lane-minor]
     const double2* __restrict__ s_rys = brick_smem;
     rys_table_to_smem<S::NROOTS>(brick_smem);
-    double* __restrict__ s_bra = reinterpret_cast<double*>(brick_smem) + P::RYS_BYTES / sizeof(double) +
-                                 (size_t)warp * (BRA_PRIM_DOUBLES + 32 * P::SLOTS);
-    double* __restrict__ slot = s_bra + BRA_PRIM_DOUBLES + lane;
-    const int npij = a.npi * a.npj;
+    double* __restrict__ slot = reinterpret_cast<double*>(brick_smem) + P::RYS_BYTES / sizeof(double) +
+                                (size_t)warp * 32 * P::SLOTS + lane;
+    const int npij = a.npi * a.npj, npkl = a.npk * a.npl;
 #define SLOT_(x) slot[(x) * 32]
     unsigned long long nq = 0;
 
@@ -296,6 +260,7 @@ jk_brick_kernel(const BrickArgs a)
         const int k0 = (int)rk.w, l0 = (int)rl.w;
         const float d_kl = a.logd[(size_t)ksh * nbas + lsh];
         const double* __restrict__ dm = a.dm;
+        const double* __restrict__ ket = a.ket_tab + (size_t)pp * npkl * 8;
 
         double jkl[DO_J ? NFK * NFL : 1];
         double dlk_r[(DO_J && P::DLK_MODE == 0) ? NFK * NFL : 1];
@@ -387,9 +352,9 @@ jk_brick_kernel(const BrickArgs a)
                 if (ish == jsh) fac *= 0.5;
                 if (ksh == lsh) fac *= 0.5;
                 if (ish == ksh && jsh == lsh) fac *= 0.5;
-                stage_bra_prims(s_bra, bi, bj, ri, rj, a.npi, a.npj, lane);
                 double eri[N];
-                eri_block_regs<LI, LJ, LK, LL>(eri, s_bra, bk, bl, ri, rj, rk, rl, npij, a.npk, a.npl, a.omega, fac, s_rys);
+                eri_block_regs<LI, LJ, LK, LL>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
+                                               npkl, a.omega, fac, s_rys);
 #define ERI_(i, j, k, l) eri[(((i) * NFJ + (j)) * NFK + (k)) * NFL + (l)]
                 if constexpr (DO_J) {
                     // J_kl += sum_ij (ij|kl) D[j,i]: lane-stationary

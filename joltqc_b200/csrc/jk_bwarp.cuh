@@ -49,10 +49,10 @@ struct BWarpPlan {
         return pg;
     }
     static constexpr int PER_GROUP = per_group();
-    // per-warp shared memory: bra primitive pairs + D_ji + the groups
-    static constexpr int OFF_DJI = BRA_PRIM_DOUBLES;
+    // per-warp shared memory: D_ji + the groups
+    static constexpr int OFF_DJI = 0;
     static constexpr int OFF_GROUPS = (OFF_DJI + NIJ + 15) / 16 * 16;
-    static constexpr size_t WARP_DOUBLES = ((size_t)OFF_GROUPS + (size_t)QPW * PER_GROUP + 3) / 4 * 4;   // 32-byte aligned warps (double4 loads of s_bra)
+    static constexpr size_t WARP_DOUBLES = ((size_t)OFF_GROUPS + (size_t)QPW * PER_GROUP + 3) / 4 * 4;
     static constexpr size_t WARP_BYTES = WARP_DOUBLES * sizeof(double);
     static constexpr int nwarps()
     {
@@ -90,7 +90,6 @@ jk_bwarp_kernel(const BrickArgs a)
     const int grp = lane / T, t = lane - grp * T;
     const bool lane_ok = grp < QPW;
     double* __restrict__ sw = smem + (size_t)warp * P::WARP_DOUBLES;
-    double* __restrict__ s_bra = sw;
     double* __restrict__ s_dji = sw + P::OFF_DJI;
     double* __restrict__ sg = sw + P::OFF_GROUPS + (size_t)(lane_ok ? grp : 0) * P::PER_GROUP;
     double* __restrict__ s_rw = sg + P::OFF_RW;
@@ -110,8 +109,8 @@ jk_bwarp_kernel(const BrickArgs a)
     const float log_max = ordered_to_float(*a.log_max_ordered);
     const float dmaxf = fmaxf(log_max, -36.8f);
     const double paircut = log(1e-13) - (double)log_max;
-    const int npij = a.npi * a.npj;
-    const bool single_prim = npij * a.npk * a.npl == 1;
+    const int npij = a.npi * a.npj, npkl = a.npk * a.npl;
+    const bool single_prim = npij * npkl == 1;
     const unsigned ntask = (unsigned)a.n_blk * (unsigned)a.n_ichunk * (unsigned)a.jsplit;
     unsigned long long nq = 0;
 
@@ -159,8 +158,8 @@ jk_bwarp_kernel(const BrickArgs a)
         const double4 rl = *reinterpret_cast<const double4*>(bl);
         const int k0 = (int)rk.w, l0 = (int)rl.w;
         const double rlrk[3] = {rl.x - rk.x, rl.y - rk.y, rl.z - rk.z};
-        const double rr_kl = rlrk[0] * rlrk[0] + rlrk[1] * rlrk[1] + rlrk[2] * rlrk[2];
         const float d_kl = a.logd[(size_t)ksh * nbas + lsh];
+        const double* __restrict__ ket = a.ket_tab + (size_t)pp * npkl * 8;
 
         double jkl[NKLP], dlk[NKLP];
 #pragma unroll
@@ -238,8 +237,9 @@ jk_bwarp_kernel(const BrickArgs a)
                 if (ish == ksh && jsh == lsh) fac *= 0.5;
                 const double rjri[3] = {rj.x - ri.x, rj.y - ri.y, rj.z - ri.z};
 
-                // per-step staging: bra primitive pairs and D_ji (one copy per warp), D_jl / D_jk (per group)
-                stage_bra_prims(s_bra, bi, bj, ri, rj, a.npi, a.npj, lane);     // leading + trailing __syncwarp
+                // per-step staging: D_ji (one copy per warp), D_jl / D_jk (per group)
+                const double* __restrict__ bra = a.bra_tab + (size_t)(e - a.j_base) * npij * 8;
+                __syncwarp();                                   // readers of the previous step are done
 #pragma unroll
                 for (int m2 = 0; m2 < (NIJ + 31) / 32; m2++) {
                     const int x = lane + m2 * 32;
@@ -263,21 +263,16 @@ jk_bwarp_kernel(const BrickArgs a)
                         for (int x = 0; x < NJC * NFI; x++) acc[s][x] = 0.0;
 
 #pragma unroll 1
-                    for (int kp = 0; kp < a.npk; kp++)
-#pragma unroll 1
-                    for (int lp = 0; lp < a.npl; lp++) {
-                        const double2 cek = *reinterpret_cast<const double2*>(bk + 4 + 2 * kp);
-                        const double2 cel = *reinterpret_cast<const double2*>(bl + 4 + 2 * lp);
-                        const double akl = cek.y + cel.y;
-                        const double inv_akl = 1.0 / akl;
-                        const double al_akl = cel.y * inv_akl;
-                        const double ckcl = cek.x * cel.x * exp(-cek.y * al_akl * rr_kl);
-                        const double qx = fma(rlrk[0], al_akl, rk.x), qy = fma(rlrk[1], al_akl, rk.y), qz = fma(rlrk[2], al_akl, rk.z);
+                    for (int klp = 0; klp < npkl; klp++) {
+                        const double4 kt0 = *reinterpret_cast<const double4*>(ket + klp * 8);
+                        const double4 kt1 = *reinterpret_cast<const double4*>(ket + klp * 8 + 4);
+                        const double akl = kt0.x, inv_akl = kt0.y, al_akl = kt0.z, ckcl = kt0.w;
+                        const double qx = kt1.x, qy = kt1.y, qz = kt1.z;
 #pragma unroll 1
                         for (int ipj = 0; ipj < npij; ipj++) {
                             __syncwarp();   // staging visible; previous product phase has finished reading g
-                            const double4 b0 = *reinterpret_cast<const double4*>(s_bra + ipj * 8);
-                            const double4 b1 = *reinterpret_cast<const double4*>(s_bra + ipj * 8 + 4);
+                            const double4 b0 = *reinterpret_cast<const double4*>(bra + ipj * 8);
+                            const double4 b1 = *reinterpret_cast<const double4*>(bra + ipj * 8 + 4);
                             const double aij = b0.x, inv_aij = b0.y, aj_aij = b0.z;
                             const double cicj = fac * b0.w;
                             const double Rpq[3] = {b1.x - qx, b1.y - qy, b1.z - qz};
