@@ -35,6 +35,8 @@ struct BrickArgs {
     const float* __restrict__ logd;           // nbas x nbas log density pool (jk.py:179-184)
     const int* __restrict__ log_max_ordered;
     float cutoff;                             // log(cutoff): evaluate quartets whose estimate is above
+    float cutoff_hi;                          // ... and not above this (+inf unless this launch is the FP32 band)
+    const float* __restrict__ dm32;           // float copy of dm (FP32-band launches only)
     // ket side: ordered pair list of the (gk, gl) group pair
     const ushort2* __restrict__ kl;
     const float* __restrict__ kl_q;           // q of the pair
@@ -158,20 +160,158 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
     }
 }
 
+// Same quartet in FP32 (mixed-precision band; the reference instantiates its kernel with DataType =
+// float, jqc/pyscf/jk.py:241-262).  Shell-centre and primitive-centre differences are formed in FP64
+// from the FP64 tables and rounded once, everything after that is float.
+template <class R, int LI, int LJ, int LK, int LL>
+__device__ __forceinline__ void fill_g_t(R* __restrict__ g, const R seed0, const R seed1, const R seed2, const R* c0,
+                                         const R* cp, const R b10, const R b01, const R b00, const R* rjri, const R* rlrk)
+{
+    using S = QuartetShape<LI, LJ, LK, LL>;
+    constexpr int GS = S::GSIZE, DJ = S::DJ, DK = S::DK, DL = S::DL, LIJ = S::LIJ, LKL = S::LKL;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        R* gd = g + d * GS;
+        gd[0] = d == 0 ? seed0 : (d == 1 ? seed1 : seed2);
+        if constexpr (LIJ > 0) {
+            gd[1] = c0[d] * gd[0];
+#pragma unroll
+            for (int i = 1; i < LIJ; i++) gd[i + 1] = c0[d] * gd[i] + (R(i) * b10) * gd[i - 1];
+        }
+        if constexpr (LKL > 0) {
+#pragma unroll
+            for (int i = 0; i <= LIJ; i++) {
+                R v = cp[d] * gd[i];
+                if (i > 0) v += R(i) * b00 * gd[i - 1];
+                gd[i + DK] = v;
+            }
+#pragma unroll
+            for (int k = 1; k < LKL; k++) {
+                const R kb01 = R(k) * b01;
+#pragma unroll
+                for (int i = 0; i <= LIJ; i++) {
+                    R v = cp[d] * gd[i + k * DK] + kb01 * gd[i + (k - 1) * DK];
+                    if (i > 0) v += R(i) * b00 * gd[i - 1 + k * DK];
+                    gd[i + (k + 1) * DK] = v;
+                }
+            }
+        }
+        if constexpr (LJ > 0) {
+            const R ab = rjri[d];
+#pragma unroll
+            for (int k = 0; k <= LKL; k++)
+#pragma unroll
+                for (int j = 0; j < LJ; j++)
+#pragma unroll
+                    for (int i = LIJ - j - 1; i >= 0; i--) {
+                        const int src = i + j * DJ + k * DK;
+                        gd[src + DJ] = gd[src + 1] - ab * gd[src];
+                    }
+        }
+        if constexpr (LL > 0) {
+            const R cd = rlrk[d];
+#pragma unroll
+            for (int ij = 0; ij < DK; ij++)
+#pragma unroll
+                for (int l = 0; l < LL; l++)
+#pragma unroll
+                    for (int k = LKL - l - 1; k >= 0; k--) {
+                        const int src = ij + k * DK + l * DL;
+                        gd[src + DL] = gd[src + DK] - cd * gd[src];
+                    }
+        }
+    }
+}
+
+template <int LI, int LJ, int LK, int LL>
+__device__ __forceinline__ void eri_block_regs_f(float* __restrict__ eri, const double* __restrict__ bra,
+                                                 const double* __restrict__ ket, const double4 ri, const double4 rj,
+                                                 const double4 rk, const double4 rl, const int npij, const int npkl,
+                                                 const float omega, const float fac, const float2* __restrict__ s_rys)
+{
+    using S = QuartetShape<LI, LJ, LK, LL>;
+    constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
+    constexpr int NROOTS = S::NROOTS, GS = S::GSIZE, DJ = S::DJ, DK = S::DK, DL = S::DL;
+    const float rjri[3] = {(float)(rj.x - ri.x), (float)(rj.y - ri.y), (float)(rj.z - ri.z)};
+    const float rlrk[3] = {(float)(rl.x - rk.x), (float)(rl.y - rk.y), (float)(rl.z - rk.z)};
+#pragma unroll
+    for (int n = 0; n < N; n++) eri[n] = 0.0f;
+#pragma unroll 1
+    for (int klp = 0; klp < npkl; klp++) {
+        const double4 k0 = *reinterpret_cast<const double4*>(ket + klp * 8);
+        const double4 k1 = *reinterpret_cast<const double4*>(ket + klp * 8 + 4);
+        const float akl = (float)k0.x, inv_akl = (float)k0.y, al_akl = (float)k0.z, ckcl = (float)k0.w;
+#pragma unroll 1
+        for (int ipj = 0; ipj < npij; ipj++) {
+            const double4 b0 = *reinterpret_cast<const double4*>(bra + ipj * 8);
+            const double4 b1 = *reinterpret_cast<const double4*>(bra + ipj * 8 + 4);
+            const float aij = (float)b0.x, inv_aij = (float)b0.y, aj_aij = (float)b0.z;
+            const float cicj = fac * (float)b0.w;
+            const float Rpq[3] = {(float)(b1.x - k1.x), (float)(b1.y - k1.y), (float)(b1.z - k1.z)};
+            const float rr = Rpq[0] * Rpq[0] + Rpq[1] * Rpq[1] + Rpq[2] * Rpq[2];
+            const float inv_aijkl = 1.0f / (aij + akl);
+            const float theta = aij * akl * inv_aijkl;
+            const float gy0 = cicj * inv_aij * inv_akl * sqrtf(inv_aijkl);
+            float rw[2 * NROOTS];
+            float theta_fac = 1.0f, sqrt_theta_fac = 1.0f;
+            if (omega > 0.0f) {
+                const float o2 = omega * omega;
+                theta_fac = o2 / (o2 + theta);
+                sqrt_theta_fac = sqrtf(theta_fac);
+            }
+            rys_roots_smem_f<NROOTS>(rr * theta * theta_fac, rw, s_rys);
+#pragma unroll 1
+            for (int ir = 0; ir < NROOTS; ir++) {
+                const float rt = rw[2 * ir] * theta_fac;
+                const float wt = rw[2 * ir + 1] * sqrt_theta_fac;
+                const float rt_aa = rt * inv_aijkl;
+                const float rt_aij = rt_aa * akl, rt_akl = rt_aa * aij;
+                const float b10 = 0.5f * inv_aij * (1.0f - rt_aij);
+                const float b01 = 0.5f * inv_akl * (1.0f - rt_akl);
+                const float b00 = 0.5f * rt_aa;
+                float c0[3], cp[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    c0[d] = fmaf(rjri[d], aj_aij, -rt_aij * Rpq[d]);
+                    cp[d] = fmaf(rlrk[d], al_akl, rt_akl * Rpq[d]);
+                }
+                float g[3 * GS];
+                fill_g_t<float, LI, LJ, LK, LL>(g, ckcl, gy0, wt, c0, cp, b10, b01, b00, rjri, rlrk);
+#pragma unroll
+                for (int i = 0; i < NFI; i++)
+#pragma unroll
+                for (int j = 0; j < NFJ; j++)
+#pragma unroll
+                for (int k = 0; k < NFK; k++)
+#pragma unroll
+                for (int l = 0; l < NFL; l++) {
+                    const int ax = CART_X[LI][i] + CART_X[LJ][j] * DJ + CART_X[LK][k] * DK + CART_X[LL][l] * DL;
+                    const int ay = CART_Y[LI][i] + CART_Y[LJ][j] * DJ + CART_Y[LK][k] * DK + CART_Y[LL][l] * DL;
+                    const int az = CART_Z[LI][i] + CART_Z[LJ][j] * DJ + CART_Z[LK][k] * DK + CART_Z[LL][l] * DL;
+                    const int n = ((i * NFJ + j) * NFK + k) * NFL + l;
+                    eri[n] = fmaf(g[ax] * g[GS + ay], g[2 * GS + az], eri[n]);
+                }
+            }
+        }
+    }
+}
+
 // Per-class layout of the brick kernel, usable at compile time (BrickPlan) and by the host (which
-// classes are supported, how much dynamic shared memory a launch needs).
+// classes are supported, how much dynamic shared memory a launch needs).  f32 = the FP32-band
+// variant: integrals, g arrays, density blocks and the Rys table are float (half the registers and
+// shared memory), the stationary J/K sums stay double.
 struct BrickShape {
     int n, nki, njkl, nroots;
     bool acc_smem;      // per-i K accumulators in lane-private shared memory (else registers)
     bool di_smem;       // D_il / D_ik blocks (stationary over the j loop) staged in lane-private shared memory
     int dlk_mode;       // D_lk block (stationary over the brick): 0 registers, 1 lane-private shared memory, 2 reloaded
-    int slots;          // lane-private doubles per lane
+    int acc_slots, d_slots;   // lane-private doubles (accumulators) and reals (density blocks) per lane
     int regs, minb, nwarps;
     size_t rys_bytes, smem;
     bool fits;
 };
 
-__host__ __device__ constexpr BrickShape brick_shape(int li, int lj, int lk, int ll)
+__host__ __device__ constexpr BrickShape brick_shape(int li, int lj, int lk, int ll, bool f32 = false)
 {
     BrickShape b{};
     const int nfi = nf_of(li), nfj = nf_of(lj), nfk = nf_of(lk), nfl = nf_of(ll);
@@ -180,37 +320,56 @@ __host__ __device__ constexpr BrickShape brick_shape(int li, int lj, int lk, int
     b.njkl = nfk * nfl;
     b.nroots = (li + lj + lk + ll) / 2 + 1;
     b.nwarps = 4;
-    const int live = b.n + b.nki + b.njkl;
-    b.acc_smem = live > 80 && b.nki > 12;
-    b.di_smem = b.nki <= 48;
     b.dlk_mode = b.njkl <= 3 ? 0 : (b.njkl <= 9 ? 1 : 2);
-    b.slots = (b.acc_smem ? b.nki : 0) + (b.di_smem ? b.nki : 0) + (b.dlk_mode == 1 ? b.njkl : 0);
-    // register budget per thread -> CTAs of 128 threads per SM: 255 -> 2, 168 -> 3, 128 -> 4
-    b.regs = live <= 12 ? 128 : (live <= 36 ? 168 : 255);
+    if (!f32) {
+        const int live = b.n + b.nki + b.njkl;
+        b.acc_smem = live > 80 && b.nki > 12;
+        b.di_smem = b.nki <= 48;
+        // register budget per thread -> CTAs of 128 threads per SM: 255 -> 2, 168 -> 3, 128 -> 4
+        b.regs = live <= 12 ? 128 : (live <= 36 ? 168 : 255);
+        b.rys_bytes = (size_t)b.nroots * (14 + 2 * b.nroots) * (RYS_NCOEF + 1) * 16;
+    } else {
+        // 32-bit registers: integrals + g arrays (float) + double accumulators
+        const int gs = (li + 1) * (lj + 1) * (lk + 1) * (ll + 1);
+        const int live = b.n + 3 * gs + 2 * b.njkl;
+        b.acc_smem = live + 2 * b.nki > 150 && b.nki > 12;
+        b.di_smem = b.nki <= 60;
+        const int r = live + (b.acc_smem ? 0 : 2 * b.nki);
+        b.regs = r <= 56 ? 128 : (r <= 100 ? 168 : 255);
+        b.rys_bytes = ((size_t)b.nroots * (14 + 2 * b.nroots) * (RYS_NCOEF + 1) * 8 + 15) / 16 * 16;
+    }
+    b.acc_slots = b.acc_smem ? b.nki : 0;
+    b.d_slots = (b.di_smem ? b.nki : 0) + (b.dlk_mode == 1 ? b.njkl : 0);
     b.minb = 65536 / (b.regs * b.nwarps * 32);
-    b.rys_bytes = (size_t)b.nroots * (14 + 2 * b.nroots) * (RYS_NCOEF + 1) * 16;
-    b.smem = b.rys_bytes + (size_t)b.nwarps * 32 * b.slots * sizeof(double);
+    b.smem = b.rys_bytes + (size_t)b.nwarps * 32 * (b.acc_slots * sizeof(double) + b.d_slots * (f32 ? 4 : 8));
     b.fits = b.n <= JQC_SMALL_N && b.smem * b.minb <= 216 * 1024;
     return b;
 }
 
-template <int LI, int LJ, int LK, int LL>
+template <class R, int LI, int LJ, int LK, int LL>
 struct BrickPlan {
-    static constexpr BrickShape B = brick_shape(LI, LJ, LK, LL);
-    static constexpr int NKI = B.nki, NJKL = B.njkl, NWARPS = B.nwarps, MINB = B.minb, SLOTS = B.slots;
+    static constexpr bool F32 = sizeof(R) == 4;
+    static constexpr BrickShape B = brick_shape(LI, LJ, LK, LL, F32);
+    static constexpr int NKI = B.nki, NJKL = B.njkl, NWARPS = B.nwarps, MINB = B.minb;
+    static constexpr int ACC_SLOTS = B.acc_slots, D_SLOTS = B.d_slots;
     static constexpr bool ACC_SMEM = B.acc_smem, DI_SMEM = B.di_smem, FITS = B.fits;
     static constexpr int DLK_MODE = B.dlk_mode;
     static constexpr size_t SMEM = B.smem, RYS_BYTES = B.rys_bytes;
-    // slot offsets (lane-private doubles)
-    static constexpr int S_ACC = 0, S_DI = ACC_SMEM ? NKI : 0, S_DLK = S_DI + (DI_SMEM ? NKI : 0);
+    // density-block slot offsets (lane-private reals)
+    static constexpr int S_DI = 0, S_DLK = DI_SMEM ? NKI : 0;
 };
 
-template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K>
-__global__ void __launch_bounds__(BrickPlan<LI, LJ, LK, LL>::NWARPS * 32, BrickPlan<LI, LJ, LK, LL>::MINB)
+template <class R> struct BrickRysTab { using type = double2; };
+template <> struct BrickRysTab<float> { using type = float2; };
+
+template <class R, int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K>
+__global__ void __launch_bounds__(BrickPlan<R, LI, LJ, LK, LL>::NWARPS * 32, BrickPlan<R, LI, LJ, LK, LL>::MINB)
 jk_brick_kernel(const BrickArgs a)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
-    using P = BrickPlan<LI, LJ, LK, LL>;
+    using P = BrickPlan<R, LI, LJ, LK, LL>;
+    using RysT = typename BrickRysTab<R>::type;
+    constexpr bool F32 = P::F32;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double2 brick_smem[];
@@ -221,13 +380,24 @@ jk_brick_kernel(const BrickArgs a)
     const float dmaxf = fmaxf(log_max, -36.8f);
     const double paircut = log(1e-13) - (double)log_max;       // jk.py:185-187, 412
     const unsigned ntask = (unsigned)a.n_blk * (unsigned)a.n_ichunk * (unsigned)a.jsplit;
-    // shared memory: [Rys table of this class][lane-private slots: element-major, lane-minor]
-    const double2* __restrict__ s_rys = brick_smem;
-    rys_table_to_smem<S::NROOTS>(brick_smem);
-    double* __restrict__ slot = reinterpret_cast<double*>(brick_smem) + P::RYS_BYTES / sizeof(double) +
-                                (size_t)warp * 32 * P::SLOTS + lane;
+    // shared memory: [Rys table of this class][accumulator slots (double)][density slots (R)], both
+    // element-major, lane-minor within a warp
+    const RysT* __restrict__ s_rys = reinterpret_cast<const RysT*>(brick_smem);
+    if constexpr (F32) rys_table_to_smem_f<S::NROOTS>(reinterpret_cast<float2*>(brick_smem));
+    else rys_table_to_smem<S::NROOTS>(brick_smem);
+    double* __restrict__ aslot = reinterpret_cast<double*>(reinterpret_cast<char*>(brick_smem) + P::RYS_BYTES) +
+                                 (size_t)warp * 32 * P::ACC_SLOTS + lane;
+    R* __restrict__ dslot = reinterpret_cast<R*>(reinterpret_cast<char*>(brick_smem) + P::RYS_BYTES +
+                                                 (size_t)P::NWARPS * 32 * P::ACC_SLOTS * sizeof(double)) +
+                            (size_t)warp * 32 * P::D_SLOTS + lane;
     const int npij = a.npi * a.npj, npkl = a.npk * a.npl;
-#define SLOT_(x) slot[(x) * 32]
+#define ASLOT_(x) aslot[(x) * 32]
+#define DSLOT_(x) dslot[(x) * 32]
+    // density elements in the precision of this launch
+    auto ldd = [&](size_t off) -> R {
+        if constexpr (F32) return __ldg(a.dm32 + off);
+        else return __ldg(a.dm + off);
+    };
     unsigned long long nq = 0;
 
 #pragma unroll 1
@@ -259,19 +429,18 @@ jk_brick_kernel(const BrickArgs a)
         const double4 rl = *reinterpret_cast<const double4*>(bl);
         const int k0 = (int)rk.w, l0 = (int)rl.w;
         const float d_kl = a.logd[(size_t)ksh * nbas + lsh];
-        const double* __restrict__ dm = a.dm;
         const double* __restrict__ ket = a.ket_tab + (size_t)pp * npkl * 8;
 
         double jkl[DO_J ? NFK * NFL : 1];
-        double dlk_r[(DO_J && P::DLK_MODE == 0) ? NFK * NFL : 1];
+        R dlk_r[(DO_J && P::DLK_MODE == 0) ? NFK * NFL : 1];
         if constexpr (DO_J) {
 #pragma unroll
             for (int k = 0; k < NFK; k++)
 #pragma unroll
             for (int l = 0; l < NFL; l++) {
                 jkl[k * NFL + l] = 0.0;
-                if constexpr (P::DLK_MODE == 0) dlk_r[k * NFL + l] = __ldg(dm + (size_t)(l0 + l) * nao + k0 + k);
-                if constexpr (P::DLK_MODE == 1) SLOT_(P::S_DLK + k * NFL + l) = __ldg(dm + (size_t)(l0 + l) * nao + k0 + k);
+                if constexpr (P::DLK_MODE == 0) dlk_r[k * NFL + l] = ldd((size_t)(l0 + l) * nao + k0 + k);
+                if constexpr (P::DLK_MODE == 1) DSLOT_(P::S_DLK + k * NFL + l) = ldd((size_t)(l0 + l) * nao + k0 + k);
             }
         }
         bool touched_kl = false;
@@ -302,16 +471,16 @@ jk_brick_kernel(const BrickArgs a)
                 // blocks use the same indexing in their own slot range
 #pragma unroll
                 for (int x = 0; x < P::NKI; x++) {
-                    if constexpr (P::ACC_SMEM) SLOT_(P::S_ACC + x) = 0.0;
+                    if constexpr (P::ACC_SMEM) ASLOT_(x) = 0.0;
                     else kacc[x] = 0.0;
                 }
                 if constexpr (P::DI_SMEM) {
 #pragma unroll
                     for (int i = 0; i < NFI; i++) {
 #pragma unroll
-                        for (int k = 0; k < NFK; k++) SLOT_(P::S_DI + i * NFK + k) = __ldg(dm + (size_t)(i0 + i) * nao + k0 + k);
+                        for (int k = 0; k < NFK; k++) DSLOT_(P::S_DI + i * NFK + k) = ldd((size_t)(i0 + i) * nao + k0 + k);
 #pragma unroll
-                        for (int l = 0; l < NFL; l++) SLOT_(P::S_DI + NFI * NFK + i * NFL + l) = __ldg(dm + (size_t)(i0 + i) * nao + l0 + l);
+                        for (int l = 0; l < NFL; l++) DSLOT_(P::S_DI + NFI * NFK + i * NFL + l) = ldd((size_t)(i0 + i) * nao + l0 + l);
                     }
                 }
             }
@@ -338,7 +507,9 @@ jk_brick_kernel(const BrickArgs a)
                         d_large = fmaxf(d_large, a.logd[(size_t)ish * nbas + jsh]);
                         d_large = fmaxf(d_large, d_kl);
                     }
-                    live = q_ijkl + d_large > a.cutoff;
+                    // precision band of this launch (screen_jk_tasks.cu:258-261: sel_fp64 = dq > cutoff_fp64)
+                    const float dq = q_ijkl + d_large;
+                    live = dq > a.cutoff && !(dq > a.cutoff_hi);
                 }
                 const unsigned m = __ballot_sync(FULL, live);
                 if (m == 0) continue;
@@ -348,43 +519,56 @@ jk_brick_kernel(const BrickArgs a)
                 const double* __restrict__ bj = a.basis + jsh * BASIS_STRIDE;
                 const double4 rj = *reinterpret_cast<const double4*>(bj);
                 const int j0 = (int)rj.w;
-                double fac = live ? PI_FAC : 0.0;
-                if (ish == jsh) fac *= 0.5;
-                if (ksh == lsh) fac *= 0.5;
-                if (ish == ksh && jsh == lsh) fac *= 0.5;
-                double eri[N];
-                eri_block_regs<LI, LJ, LK, LL>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
-                                               npkl, a.omega, fac, s_rys);
+                R fac = live ? R(PI_FAC) : R(0);
+                if (ish == jsh) fac *= R(0.5);
+                if (ksh == lsh) fac *= R(0.5);
+                if (ish == ksh && jsh == lsh) fac *= R(0.5);
+                R eri[N];
+                if constexpr (F32)
+                    eri_block_regs_f<LI, LJ, LK, LL>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
+                                                     npkl, (float)a.omega, fac, s_rys);
+                else
+                    eri_block_regs<LI, LJ, LK, LL>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
+                                                   npkl, a.omega, fac, s_rys);
 #define ERI_(i, j, k, l) eri[(((i) * NFJ + (j)) * NFK + (k)) * NFL + (l)]
                 if constexpr (DO_J) {
                     // J_kl += sum_ij (ij|kl) D[j,i]: lane-stationary
-                    double d_ji[NFI * NFJ];
+                    R d_ji[NFI * NFJ];
 #pragma unroll
                     for (int i = 0; i < NFI; i++)
 #pragma unroll
-                    for (int j = 0; j < NFJ; j++) d_ji[i * NFJ + j] = __ldg(dm + (size_t)(j0 + j) * nao + i0 + i);
+                    for (int j = 0; j < NFJ; j++) d_ji[i * NFJ + j] = ldd((size_t)(j0 + j) * nao + i0 + i);
 #pragma unroll
                     for (int k = 0; k < NFK; k++)
 #pragma unroll
                     for (int l = 0; l < NFL; l++) {
-                        double s = jkl[k * NFL + l];
+                        if constexpr (F32) {
+                            R s = R(0);
 #pragma unroll
-                        for (int i = 0; i < NFI; i++)
+                            for (int i = 0; i < NFI; i++)
 #pragma unroll
-                        for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji[i * NFJ + j], s);
-                        jkl[k * NFL + l] = s;
+                            for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji[i * NFJ + j], s);
+                            jkl[k * NFL + l] += (double)s;
+                        } else {
+                            R s = (R)jkl[k * NFL + l];
+#pragma unroll
+                            for (int i = 0; i < NFI; i++)
+#pragma unroll
+                            for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji[i * NFJ + j], s);
+                            jkl[k * NFL + l] = s;
+                        }
                     }
                     // J_ij += sum_kl (ij|kl) D[l,k]: one address for the whole warp -> reduce-scatter
-                    double vij[NFI * NFJ];
+                    R vij[NFI * NFJ];
 #pragma unroll
-                    for (int x = 0; x < NFI * NFJ; x++) vij[x] = 0.0;
+                    for (int x = 0; x < NFI * NFJ; x++) vij[x] = R(0);
 #pragma unroll
                     for (int k = 0; k < NFK; k++)
 #pragma unroll
                     for (int l = 0; l < NFL; l++) {
-                        const double d = P::DLK_MODE == 0 ? dlk_r[P::DLK_MODE == 0 ? k * NFL + l : 0]
-                                       : (P::DLK_MODE == 1 ? SLOT_(P::S_DLK + k * NFL + l)
-                                                           : __ldg(dm + (size_t)(l0 + l) * nao + k0 + k));
+                        const R d = P::DLK_MODE == 0 ? dlk_r[P::DLK_MODE == 0 ? k * NFL + l : 0]
+                                  : (P::DLK_MODE == 1 ? DSLOT_(P::S_DLK + k * NFL + l)
+                                                      : ldd((size_t)(l0 + l) * nao + k0 + k));
 #pragma unroll
                         for (int i = 0; i < NFI; i++)
 #pragma unroll
@@ -396,46 +580,46 @@ jk_brick_kernel(const BrickArgs a)
                     for (int x = 0; x < warp_rs_final(NFI * NFJ); x++)
                         if (x < cnt) {
                             const int i = (idx + x) / NFJ, j = (idx + x) - i * NFJ;
-                            atomicAdd(a.vj + (size_t)(j0 + j) * nao + i0 + i, vij[x]);
+                            atomicAdd(a.vj + (size_t)(j0 + j) * nao + i0 + i, (double)vij[x]);
                         }
                 }
                 if constexpr (DO_K) {
                     {   // K_ik += sum_jl (ij|kl) D[j,l]: stationary over the j loop
-                        double d[NFJ * NFL];
+                        R d[NFJ * NFL];
 #pragma unroll
                         for (int j = 0; j < NFJ; j++)
 #pragma unroll
-                        for (int l = 0; l < NFL; l++) d[j * NFL + l] = __ldg(dm + (size_t)(j0 + j) * nao + l0 + l);
+                        for (int l = 0; l < NFL; l++) d[j * NFL + l] = ldd((size_t)(j0 + j) * nao + l0 + l);
 #pragma unroll
                         for (int i = 0; i < NFI; i++)
 #pragma unroll
                         for (int k = 0; k < NFK; k++) {
-                            double s = 0.0;
+                            R s = R(0);
 #pragma unroll
                             for (int j = 0; j < NFJ; j++)
 #pragma unroll
                             for (int l = 0; l < NFL; l++) s = fma(ERI_(i, j, k, l), d[j * NFL + l], s);
-                            if constexpr (P::ACC_SMEM) SLOT_(P::S_ACC + i * NFK + k) += s;
-                            else kacc[i * NFK + k] += s;
+                            if constexpr (P::ACC_SMEM) ASLOT_(i * NFK + k) += (double)s;
+                            else kacc[i * NFK + k] += (double)s;
                         }
                     }
                     {   // K_il += sum_jk (ij|kl) D[j,k]: stationary over the j loop
-                        double d[NFJ * NFK];
+                        R d[NFJ * NFK];
 #pragma unroll
                         for (int j = 0; j < NFJ; j++)
 #pragma unroll
-                        for (int k = 0; k < NFK; k++) d[j * NFK + k] = __ldg(dm + (size_t)(j0 + j) * nao + k0 + k);
+                        for (int k = 0; k < NFK; k++) d[j * NFK + k] = ldd((size_t)(j0 + j) * nao + k0 + k);
 #pragma unroll
                         for (int i = 0; i < NFI; i++)
 #pragma unroll
                         for (int l = 0; l < NFL; l++) {
-                            double s = 0.0;
+                            R s = R(0);
 #pragma unroll
                             for (int j = 0; j < NFJ; j++)
 #pragma unroll
                             for (int k = 0; k < NFK; k++) s = fma(ERI_(i, j, k, l), d[j * NFK + k], s);
-                            if constexpr (P::ACC_SMEM) SLOT_(P::S_ACC + NFI * NFK + i * NFL + l) += s;
-                            else kacc[NFI * NFK + i * NFL + l] += s;
+                            if constexpr (P::ACC_SMEM) ASLOT_(NFI * NFK + i * NFL + l) += (double)s;
+                            else kacc[NFI * NFK + i * NFL + l] += (double)s;
                         }
                     }
                     {   // K_jk += sum_il (ij|kl) D[i,l]: scattered per quartet
@@ -443,16 +627,16 @@ jk_brick_kernel(const BrickArgs a)
                         for (int j = 0; j < NFJ; j++)
 #pragma unroll
                         for (int k = 0; k < NFK; k++) {
-                            double s = 0.0;
+                            R s = R(0);
 #pragma unroll
                             for (int i = 0; i < NFI; i++)
 #pragma unroll
                             for (int l = 0; l < NFL; l++) {
-                                const double d = P::DI_SMEM ? SLOT_(P::S_DI + NFI * NFK + i * NFL + l)
-                                                            : __ldg(dm + (size_t)(i0 + i) * nao + l0 + l);
+                                const R d = P::DI_SMEM ? DSLOT_(P::S_DI + NFI * NFK + i * NFL + l)
+                                                       : ldd((size_t)(i0 + i) * nao + l0 + l);
                                 s = fma(ERI_(i, j, k, l), d, s);
                             }
-                            if (live) atomicAdd(a.vk + (size_t)(j0 + j) * nao + k0 + k, s);
+                            if (live) atomicAdd(a.vk + (size_t)(j0 + j) * nao + k0 + k, (double)s);
                         }
                     }
                     {   // K_jl += sum_ik (ij|kl) D[i,k]: scattered per quartet
@@ -460,16 +644,16 @@ jk_brick_kernel(const BrickArgs a)
                         for (int j = 0; j < NFJ; j++)
 #pragma unroll
                         for (int l = 0; l < NFL; l++) {
-                            double s = 0.0;
+                            R s = R(0);
 #pragma unroll
                             for (int i = 0; i < NFI; i++)
 #pragma unroll
                             for (int k = 0; k < NFK; k++) {
-                                const double d = P::DI_SMEM ? SLOT_(P::S_DI + i * NFK + k)
-                                                            : __ldg(dm + (size_t)(i0 + i) * nao + k0 + k);
+                                const R d = P::DI_SMEM ? DSLOT_(P::S_DI + i * NFK + k)
+                                                       : ldd((size_t)(i0 + i) * nao + k0 + k);
                                 s = fma(ERI_(i, j, k, l), d, s);
                             }
-                            if (live) atomicAdd(a.vk + (size_t)(j0 + j) * nao + l0 + l, s);
+                            if (live) atomicAdd(a.vk + (size_t)(j0 + j) * nao + l0 + l, (double)s);
                         }
                     }
                 }
@@ -482,14 +666,14 @@ jk_brick_kernel(const BrickArgs a)
                     for (int i = 0; i < NFI; i++)
 #pragma unroll
                     for (int k = 0; k < NFK; k++) {
-                        const double v = P::ACC_SMEM ? SLOT_(P::S_ACC + i * NFK + k) : kacc[P::ACC_SMEM ? 0 : i * NFK + k];
+                        const double v = P::ACC_SMEM ? ASLOT_(i * NFK + k) : kacc[P::ACC_SMEM ? 0 : i * NFK + k];
                         atomicAdd(a.vk + (size_t)(i0 + i) * nao + k0 + k, v);
                     }
 #pragma unroll
                     for (int i = 0; i < NFI; i++)
 #pragma unroll
                     for (int l = 0; l < NFL; l++) {
-                        const double v = P::ACC_SMEM ? SLOT_(P::S_ACC + NFI * NFK + i * NFL + l)
+                        const double v = P::ACC_SMEM ? ASLOT_(NFI * NFK + i * NFL + l)
                                                      : kacc[P::ACC_SMEM ? 0 : NFI * NFK + i * NFL + l];
                         atomicAdd(a.vk + (size_t)(i0 + i) * nao + l0 + l, v);
                     }
@@ -506,7 +690,8 @@ jk_brick_kernel(const BrickArgs a)
             }
         }
     }
-#undef SLOT_
+#undef ASLOT_
+#undef DSLOT_
     if (lane == 0 && nq) atomicAdd(a.qcount, nq);
 }
 

@@ -43,24 +43,10 @@ __device__ __forceinline__ void rys_root_one(double x, int i, double& root, doub
         weight = RYS_LARGEX[(TRI + i) * 2 + 1] * (SQRTPIE4 * sqrt(inv_x));
         return;
     }
-    const int it = (int)(x * 0.4);
-    const double u = fma(x - it * 2.5, 0.8, -1.0);
-    const double u2 = 2.0 * u;
-    const double2* __restrict__ c = reinterpret_cast<const double2*>(RYS_CHEB + RYS_CHEB_OFFSET[NROOTS - 1]) +
-                                    ((size_t)it * NROOTS + i) * RYS_NCOEF;
-    double2 a = __ldg(c + RYS_NCOEF - 1);
-    double r1 = a.x, w1 = a.y, r2 = 0.0, w2 = 0.0;
-#pragma unroll
-    for (int k = RYS_NCOEF - 2; k >= 1; k--) {
-        a = __ldg(c + k);
-        const double r0 = fma(u2, r1, a.x) - r2;
-        const double w0 = fma(u2, w1, a.y) - w2;
-        r2 = r1; r1 = r0;
-        w2 = w1; w1 = w0;
-    }
-    a = __ldg(c);
-    root = fma(u, r1, a.x) - r2;
-    weight = fma(u, w1, a.y) - w2;
+    const RysPowers p = rys_powers(x);
+    const double2* __restrict__ c = reinterpret_cast<const double2*>(RYS_MONO + RYS_CHEB_OFFSET[NROOTS - 1]) +
+                                    ((size_t)p.it * NROOTS + i) * RYS_NCOEF;
+    rys_estrin(c, p, root, weight, RysLdg());
 }
 
 // Same, from the shared-memory copy of the table (RysSmem layout, jqc_common.cuh).
@@ -77,23 +63,8 @@ __device__ __forceinline__ void rys_root_one_smem(double x, int i, double& root,
         weight = RYS_LARGEX[(TRI + i) * 2 + 1] * (SQRTPIE4 * sqrt(inv_x));
         return;
     }
-    const int it = (int)(x * 0.4);
-    const double u = fma(x - it * 2.5, 0.8, -1.0);
-    const double u2 = 2.0 * u;
-    const double2* __restrict__ c = s_tab + (i * T::NINT + it) * T::ROW;
-    double2 a = c[RYS_NCOEF - 1];
-    double r1 = a.x, w1 = a.y, r2 = 0.0, w2 = 0.0;
-#pragma unroll
-    for (int k = RYS_NCOEF - 2; k >= 1; k--) {
-        a = c[k];
-        const double r0 = fma(u2, r1, a.x) - r2;
-        const double w0 = fma(u2, w1, a.y) - w2;
-        r2 = r1; r1 = r0;
-        w2 = w1; w1 = w0;
-    }
-    a = c[0];
-    root = fma(u, r1, a.x) - r2;
-    weight = fma(u, w1, a.y) - w2;
+    const RysPowers p = rys_powers(x);
+    rys_estrin(s_tab + (i * T::NINT + p.it) * T::ROW, p, root, weight, RysLds());
 }
 
 // TRR + HRR for one cartesian direction with the recurrences in REGISTERS: the TRR runs row by row

@@ -74,11 +74,57 @@ struct ShellHead {
 
 // ---------------------------------------------------------------------------------------
 // Rys roots (t^2) and weights for NROOTS points at argument x (already theta-scaled).
-// Two regimes only: Chebyshev interval table (the first interval covers x -> 0, so no
-// small-x branch) and the Hermite asymptote for x >= 35 + 5 n.  Same tables and accuracy
-// class as the reference's rys_roots (jqc/backend/rys/rys_roots.cu:29-160); the range
-// separation scaling for omega > 0 follows :42-47.
+// Two regimes only: the interval table (the first interval covers x -> 0, so no small-x branch)
+// and the Hermite asymptote for x >= 35 + 5 n.  Same fit and accuracy class as the reference's
+// rys_roots (jqc/backend/rys/rys_roots.cu:29-160); the range separation scaling for omega > 0
+// follows :42-47.  The reference evaluates each degree-13 series with a Clenshaw recurrence
+// (rys_roots.cu:110-140): 26 dependent FP64 operations per value.  Here the fit is stored in the
+// power basis (tools/gen_rys_tables.py) and evaluated with Estrin's scheme: 13 FMAs of depth 4 on
+// u, u^2, u^4, u^8 shared by all 2 n series of a quartet, so the evaluation is throughput- and not
+// latency-bound at the 2-4 resident warps per scheduler these kernels run with.
 // rw[2i] = root, rw[2i+1] = weight.
+struct RysPowers {
+    double u, u2, u4, u8;
+    int it;
+};
+__device__ __forceinline__ RysPowers rys_powers(double x)
+{
+    RysPowers p;
+    p.it = (int)(x * 0.4);
+    p.u = fma(x - p.it * 2.5, 0.8, -1.0);
+    p.u2 = p.u * p.u;
+    p.u4 = p.u2 * p.u2;
+    p.u8 = p.u4 * p.u4;
+    return p;
+}
+// one (root, weight) pair from its 14 coefficient pairs c[0..13]; LD(c + k) loads pair k
+template <class LD>
+__device__ __forceinline__ void rys_estrin(const double2* __restrict__ c, const RysPowers& p, double& root, double& weight, LD ld)
+{
+    static_assert(RYS_NCOEF == 14, "Estrin tree below is written for degree 13");
+    double2 a[RYS_NCOEF];
+#pragma unroll
+    for (int k = 0; k < RYS_NCOEF; k++) a[k] = ld(c + k);
+    double r[7], w[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        r[k] = fma(a[2 * k + 1].x, p.u, a[2 * k].x);
+        w[k] = fma(a[2 * k + 1].y, p.u, a[2 * k].y);
+    }
+    const double r01 = fma(r[1], p.u2, r[0]), r23 = fma(r[3], p.u2, r[2]), r45 = fma(r[5], p.u2, r[4]);
+    const double w01 = fma(w[1], p.u2, w[0]), w23 = fma(w[3], p.u2, w[2]), w45 = fma(w[5], p.u2, w[4]);
+    const double ra = fma(r23, p.u4, r01), rb = fma(r[6], p.u4, r45);
+    const double wa = fma(w23, p.u4, w01), wb = fma(w[6], p.u4, w45);
+    root = fma(rb, p.u8, ra);
+    weight = fma(wb, p.u8, wa);
+}
+struct RysLdg {
+    __device__ __forceinline__ double2 operator()(const double2* q) const { return __ldg(q); }
+};
+struct RysLds {
+    __device__ __forceinline__ double2 operator()(const double2* q) const { return *q; }
+};
+
 template <int NROOTS>
 __device__ __forceinline__ void rys_roots(double x, double* __restrict__ rw)
 {
@@ -94,32 +140,15 @@ __device__ __forceinline__ void rys_roots(double x, double* __restrict__ rw)
         }
         return;
     }
-    const int it = (int)(x * 0.4);
-    const double u = fma(x - it * 2.5, 0.8, -1.0);
-    const double u2 = 2.0 * u;
+    const RysPowers p = rys_powers(x);
     const double2* __restrict__ blk =
-        reinterpret_cast<const double2*>(RYS_CHEB + RYS_CHEB_OFFSET[NROOTS - 1]) + (size_t)it * NROOTS * RYS_NCOEF;
+        reinterpret_cast<const double2*>(RYS_MONO + RYS_CHEB_OFFSET[NROOTS - 1]) + (size_t)p.it * NROOTS * RYS_NCOEF;
 #pragma unroll
-    for (int i = 0; i < NROOTS; i++) {
-        const double2* __restrict__ c = blk + i * RYS_NCOEF;
-        double2 a = __ldg(c + RYS_NCOEF - 1);
-        double r1 = a.x, w1 = a.y, r2 = 0.0, w2 = 0.0;
-#pragma unroll
-        for (int k = RYS_NCOEF - 2; k >= 1; k--) {
-            a = __ldg(c + k);
-            const double r0 = fma(u2, r1, a.x) - r2;
-            const double w0 = fma(u2, w1, a.y) - w2;
-            r2 = r1; r1 = r0;
-            w2 = w1; w1 = w0;
-        }
-        a = __ldg(c);
-        rw[2 * i] = fma(u, r1, a.x) - r2;
-        rw[2 * i + 1] = fma(u, w1, a.y) - w2;
-    }
+    for (int i = 0; i < NROOTS; i++) rys_estrin(blk + i * RYS_NCOEF, p, rw[2 * i], rw[2 * i + 1], RysLdg());
 }
 
 // ---------------------------------------------------------------------------------------
-// Shared-memory copy of the NROOTS block of the Chebyshev table.  The per-lane interval gathers of
+// Shared-memory copy of the NROOTS block of the table.  The per-lane interval gathers of
 // rys_roots (14 coefficient pairs per root, a different interval in every lane) saturate the
 // L1/TEX path when they go to global memory (profiles/r2: 31 % of the stall samples of the
 // (ps|ps) class); from shared memory the same gathers are 16-byte LDS with rows padded to 15
@@ -136,7 +165,7 @@ template <int NROOTS>
 __device__ __forceinline__ void rys_table_to_smem(double2* __restrict__ s_tab)
 {
     using T = RysSmem<NROOTS>;
-    const double2* __restrict__ src = reinterpret_cast<const double2*>(RYS_CHEB + RYS_CHEB_OFFSET[NROOTS - 1]);
+    const double2* __restrict__ src = reinterpret_cast<const double2*>(RYS_MONO + RYS_CHEB_OFFSET[NROOTS - 1]);
     for (int idx = threadIdx.x; idx < NROOTS * T::NINT * RYS_NCOEF; idx += blockDim.x) {
         const int k = idx % RYS_NCOEF, row = idx / RYS_NCOEF;
         const int it = row / NROOTS, i = row - it * NROOTS;
@@ -161,26 +190,74 @@ __device__ __forceinline__ void rys_roots_smem(double x, double* __restrict__ rw
         }
         return;
     }
-    const int it = (int)(x * 0.4);
-    const double u = fma(x - it * 2.5, 0.8, -1.0);
-    const double u2 = 2.0 * u;
-    const double2* __restrict__ blk = s_tab + it * T::ROW;
+    const RysPowers p = rys_powers(x);
+    const double2* __restrict__ blk = s_tab + p.it * T::ROW;
+#pragma unroll
+    for (int i = 0; i < NROOTS; i++) rys_estrin(blk + i * T::NINT * T::ROW, p, rw[2 * i], rw[2 * i + 1], RysLds());
+}
+
+// ---------------------------------------------------------------------------------------
+// FP32 copy of the same table and evaluation, for the mixed-precision band (quartets whose
+// Schwarz x density estimate lies between cutoff_fp32 and cutoff_fp64; the reference evaluates
+// those with DataType = float throughout, jqc/pyscf/jk.py:241-328, rys_roots.cu with float).
+template <int NROOTS>
+struct RysSmemF {
+    static constexpr int NINT = 14 + 2 * NROOTS;
+    static constexpr int ROW = RYS_NCOEF + 1;            // padded row of float2: 15 x 8 B, odd number of 8-byte words
+    static constexpr int PAIRS = NROOTS * NINT * ROW;
+    static constexpr size_t BYTES = ((size_t)PAIRS * sizeof(float2) + 15) / 16 * 16;
+};
+
+template <int NROOTS>
+__device__ __forceinline__ void rys_table_to_smem_f(float2* __restrict__ s_tab)
+{
+    using T = RysSmemF<NROOTS>;
+    const double2* __restrict__ src = reinterpret_cast<const double2*>(RYS_MONO + RYS_CHEB_OFFSET[NROOTS - 1]);
+    for (int idx = threadIdx.x; idx < NROOTS * T::NINT * RYS_NCOEF; idx += blockDim.x) {
+        const int k = idx % RYS_NCOEF, row = idx / RYS_NCOEF;
+        const int it = row / NROOTS, i = row - it * NROOTS;
+        const double2 v = src[idx];
+        s_tab[(i * T::NINT + it) * T::ROW + k] = make_float2((float)v.x, (float)v.y);
+    }
+    __syncthreads();
+}
+
+template <int NROOTS>
+__device__ __forceinline__ void rys_roots_smem_f(float x, float* __restrict__ rw, const float2* __restrict__ s_tab)
+{
+    using T = RysSmemF<NROOTS>;
+    constexpr int TRI = NROOTS * (NROOTS - 1) / 2;
+    constexpr float large_x = NROOTS * 5 + 35;
+    if (x >= large_x) {
+        const float inv_x = 1.0f / x;
+        const float t = (float)SQRTPIE4 * sqrtf(inv_x);
+#pragma unroll
+        for (int i = 0; i < NROOTS; i++) {
+            rw[2 * i] = (float)RYS_LARGEX[(TRI + i) * 2] * inv_x;
+            rw[2 * i + 1] = (float)RYS_LARGEX[(TRI + i) * 2 + 1] * t;
+        }
+        return;
+    }
+    const int it = (int)(x * 0.4f);
+    const float u = fmaf(x - it * 2.5f, 0.8f, -1.0f);
+    const float u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
+    const float2* __restrict__ blk = s_tab + it * T::ROW;
 #pragma unroll
     for (int i = 0; i < NROOTS; i++) {
-        const double2* __restrict__ c = blk + i * T::NINT * T::ROW;
-        double2 a = c[RYS_NCOEF - 1];
-        double r1 = a.x, w1 = a.y, r2 = 0.0, w2 = 0.0;
+        const float2* __restrict__ c = blk + i * T::NINT * T::ROW;
+        float2 a[RYS_NCOEF];
 #pragma unroll
-        for (int k = RYS_NCOEF - 2; k >= 1; k--) {
-            a = c[k];
-            const double r0 = fma(u2, r1, a.x) - r2;
-            const double w0 = fma(u2, w1, a.y) - w2;
-            r2 = r1; r1 = r0;
-            w2 = w1; w1 = w0;
+        for (int k = 0; k < RYS_NCOEF; k++) a[k] = c[k];
+        float r[7], w[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            r[k] = fmaf(a[2 * k + 1].x, u, a[2 * k].x);
+            w[k] = fmaf(a[2 * k + 1].y, u, a[2 * k].y);
         }
-        a = c[0];
-        rw[2 * i] = fma(u, r1, a.x) - r2;
-        rw[2 * i + 1] = fma(u, w1, a.y) - w2;
+        const float r01 = fmaf(r[1], u2, r[0]), r23 = fmaf(r[3], u2, r[2]), r45 = fmaf(r[5], u2, r[4]);
+        const float w01 = fmaf(w[1], u2, w[0]), w23 = fmaf(w[3], u2, w[2]), w45 = fmaf(w[5], u2, w[4]);
+        rw[2 * i] = fmaf(fmaf(r[6], u4, r45), u8, fmaf(r23, u4, r01));
+        rw[2 * i + 1] = fmaf(fmaf(w[6], u4, w45), u8, fmaf(w23, u4, w01));
     }
 }
 
@@ -196,16 +273,17 @@ __host__ __device__ constexpr int warp_rs_final(int n)
 
 template <int N, int OFF>
 struct WarpReduceScatter {
-    static __device__ __forceinline__ void run(double* __restrict__ v, const int lane, int& start, int& cnt)
+    template <class R>
+    static __device__ __forceinline__ void run(R* __restrict__ v, const int lane, int& start, int& cnt)
     {
         constexpr int H = (N + 1) / 2;
         const bool up = (lane & OFF) != 0;
 #pragma unroll
         for (int e = 0; e < H; e++) {
-            const double lo = v[e];
-            const double hi = (e + H < N) ? v[e + H] : 0.0;
-            const double send = up ? lo : hi;
-            const double keep = up ? hi : lo;
+            const R lo = v[e];
+            const R hi = (e + H < N) ? v[e + H] : R(0);
+            const R send = up ? lo : hi;
+            const R keep = up ? hi : lo;
             v[e] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
         }
         if (up) { start += H; cnt -= H; }

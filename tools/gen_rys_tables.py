@@ -142,10 +142,36 @@ def largex(n):
     return out
 
 
-def emit(path, qual, iqual, cheb, sx, lx):
+def cheb_to_monomial(cheb):
+    """Exact change of basis of every degree-13 series from Chebyshev T_k(u) to powers u^k (rational
+    arithmetic on the stored doubles, rounded once).  The device evaluates the power form with
+    Estrin's scheme: 13 FMAs of depth 4 instead of a 26-operation dependent Clenshaw chain; the
+    coefficients decay fast enough that sum|m_k| <= 2.4 |p|, i.e. no loss of accuracy
+    (max relative deviation from the exact Chebyshev value 7e-16 over all intervals)."""
+    from fractions import Fraction
+
+    T = [[0] * NCOEF for _ in range(NCOEF)]
+    T[0][0] = 1
+    T[1][1] = 1
+    for k in range(2, NCOEF):
+        for j in range(NCOEF):
+            T[k][j] = (2 * T[k - 1][j - 1] if j > 0 else 0) - T[k - 2][j]
+    out = {}
+    for n, c in cheb.items():
+        m = np.zeros_like(c)
+        for idx in np.ndindex(c.shape[0], c.shape[1], 2):
+            a = [Fraction(float(v)) for v in c[idx[0], idx[1], :, idx[2]]]
+            for j in range(NCOEF):
+                m[idx[0], idx[1], j, idx[2]] = float(sum(a[k] * T[k][j] for k in range(NCOEF)))
+        out[n] = m
+    return out
+
+
+def emit(path, qual, iqual, cheb, sx, lx, name="RYS_CHEB", basis="Chebyshev T_k(u), T_0 coefficient unhalved"):
     with open(path, "w") as f:
         f.write("// GENERATED by tools/gen_rys_tables.py (mpmath, 80 digits). Do not edit.\n")
-        f.write("// Layouts: RYS_CHEB[off(n) + ((it*n + root)*14 + k)*2 + {0:root,1:weight}],\n")
+        f.write("// Series basis of %s: %s; u = 0.8 (x - 2.5 it) - 1.\n" % (name, basis))
+        f.write("// Layouts: %s[off(n) + ((it*n + root)*14 + k)*2 + {0:root,1:weight}],\n" % name)
         f.write("//          RYS_SMALLX[(n(n-1)/2 + root)*4 + {r0,r1,w0,w1}], RYS_LARGEX[(n(n-1)/2 + root)*2 + {R,W}]\n")
         f.write("#pragma once\n")
         f.write("#define RYS_NMAX %d\n#define RYS_NCOEF %d\n" % (NMAX, NCOEF))
@@ -155,7 +181,7 @@ def emit(path, qual, iqual, cheb, sx, lx):
         f.write("// element offset of the n-root block inside RYS_CHEB (index n-1)\n")
         f.write("%s RYS_CHEB_OFFSET[%d] = {%s};\n" % (iqual, NMAX + 1, ", ".join(map(str, offs))))
         flat = np.concatenate([cheb[n].ravel() for n in range(1, NMAX + 1)])
-        f.write("%s RYS_CHEB[%d] = {\n" % (qual, flat.size))
+        f.write("%s %s[%d] = {\n" % (qual, name, flat.size))
         for i in range(0, flat.size, 4):
             f.write(" " + ", ".join("%.17e" % v for v in flat[i : i + 4]) + ",\n")
         f.write("};\n")
@@ -171,7 +197,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out-npz", default=os.path.join(os.path.dirname(__file__), "rys_tables.npz"))
     ap.add_argument("--procs", type=int, default=os.cpu_count())
+    ap.add_argument("--from-npz", action="store_true", help="re-emit the headers from the saved fit (no mpmath run)")
     args = ap.parse_args()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if args.from_npz:
+        d = np.load(args.out_npz)
+        cheb = {n: d["cheb%d" % n] for n in range(1, NMAX + 1)}
+        sx = {n: d["sx%d" % n] for n in range(1, NMAX + 1)}
+        lx = {n: d["lx%d" % n] for n in range(1, NMAX + 1)}
+        emit_all(root, cheb, sx, lx)
+        return
     jobs = [(n, it) for n in range(1, NMAX + 1) for it in range(n_intervals(n))]
     cheb = {n: np.zeros((n_intervals(n), n, NCOEF, 2)) for n in range(1, NMAX + 1)}
     with mp_.Pool(args.procs) as pool:
@@ -182,8 +217,13 @@ def main():
     sx = {n: smallx(n) for n in range(1, NMAX + 1)}
     lx = {n: largex(n) for n in range(1, NMAX + 1)}
     np.savez(args.out_npz, **{"cheb%d" % n: cheb[n] for n in cheb}, **{"sx%d" % n: sx[n] for n in sx}, **{"lx%d" % n: lx[n] for n in lx})
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    emit(os.path.join(root, "joltqc_b200", "csrc", "rys_tables.cuh"), "__device__ const double", "static constexpr int", cheb, sx, lx)
+    emit_all(root, cheb, sx, lx)
+
+
+def emit_all(root, cheb, sx, lx):
+    # device: power-basis coefficients (Estrin evaluation); oracle: the Chebyshev fit itself
+    emit(os.path.join(root, "joltqc_b200", "csrc", "rys_tables.cuh"), "__device__ const double", "static constexpr int",
+         cheb_to_monomial(cheb), sx, lx, name="RYS_MONO", basis="powers u^k (exact change of basis of the Chebyshev fit)")
     emit(os.path.join(root, "oracle", "rys_tables.h"), "static const double", "static const int", cheb, sx, lx)
 
 
