@@ -280,6 +280,27 @@ def time_builds(eng, dm_dev, warmup, steps):
     return e0.elapsed_time(e1) / steps
 
 
+def mixed_leg(eng, dm_dev, vj64, vk64, cutoff_fp64=1e-7):
+    """BASELINE config 5 column "FP64 vs mixed": the same build with the FP32 band of the reference
+    (cutoff_fp32 = 1e-13 < estimate <= cutoff_fp64, jk.py:93-96) evaluated in single precision.
+    Reported separately from the FP64 headline, with its element-wise deviation from the FP64 result."""
+    import torch
+    eng.get_jk(dm_dev, hermi=1, cutoff_fp64=cutoff_fp64, cutoff_fp32=1e-13)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    vj, vk = eng.get_jk(dm_dev, hermi=1, cutoff_fp64=cutoff_fp64, cutoff_fp32=1e-13)
+    e1.record()
+    torch.cuda.synchronize()
+    (n64, n32), _ = eng.last_band_stats()
+    return {"s_per_build": e0.elapsed_time(e1) * 1e-3, "cutoff_fp64": cutoff_fp64, "cutoff_fp32": 1e-13,
+            "quartets_fp64": n64, "quartets_fp32": n32,
+            "fp32_kernels": "angular classes with <= 108 integrals (brick kernel, float integrals, FP64 accumulation); larger classes evaluate their band in FP64",
+            "max_abs_dJ_vs_fp64": float((vj - vj64).abs().max().item()), "max_abs_dK_vs_fp64": float((vk - vk64).abs().max().item()),
+            "max_abs_J": float(vj64.abs().max().item()), "max_abs_K": float(vk64.abs().max().item()),
+            "stated_tolerance": "max-abs 1e-7 x max(1, max|J|) on J and K (reference tests: 1e-7, jqc/pyscf/tests/test_jk.py:245-246)"}
+
+
 def extra_configs(peak_probe, dev):
     """The other BASELINE.json configurations, 1 warm-up + 1 timed build each (1 GPU)."""
     import torch
@@ -296,6 +317,10 @@ def extra_configs(peak_probe, dev):
         fl = total_flops(counts, pw)
         out["%s/dm=%s" % (wl, dmk)] = {"s_per_build": ms * 1e-3, "quartets": int(counts.sum()), "tflops": fl / (ms * 1e-3) / 1e12,
                                        "frac_of_fp64_peak": fl / (ms * 1e-3) / 1e12 / peak_probe}
+        if wl == "valinomycin-tzvpp":      # config 5: FP64 vs mixed
+            vj64, vk64 = eng.get_jk(dm_dev, hermi=1)
+            out["%s/dm=%s" % (wl, dmk)]["mixed_precision"] = mixed_leg(eng, dm_dev, vj64, vk64)
+            del vj64, vk64
         lay._cache.clear()
         del eng
         torch.cuda.empty_cache()
@@ -503,6 +528,8 @@ def main():
     }
     if per_rank is not None:
         line["per_rank"] = per_rank
+    if world == 1:
+        line["mixed_precision"] = mixed_leg(eng, dm_dev, vj, vk)
     if world == 1 and not args.no_extras:
         line["ref_kernels"] = ref_kernels_leg(lay, eng, dm_dev)
         if "value" in line["ref_kernels"]:

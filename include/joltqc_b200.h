@@ -83,10 +83,14 @@ int jqc_dm_to_mol(jqc_engine* eng, const double* kern_dev, int n, double* mol_de
  * for the one not requested (the reference returns the int 0 there).  hermi == 1 promises a
  * symmetric dm.  omega: 0 Coulomb, > 0 long-range erf (jk.py:133-134), < 0 -> JQC_EINVAL.
  * cutoff_fp64 / cutoff_fp32: the two screening thresholds of generate_jk_kernel
- * (jk.py:93-96); quartets with estimate above cutoff_fp32 are evaluated, all in FP64 in this
- * build (the FP32 band of the reference is evaluated in FP64 as well).
- * Work is enqueued on `stream` (cudaStream_t, NULL = default stream) without any host
- * synchronisation; results are complete when the stream reaches this point. */
+ * (jk.py:93-96; selection rule screen_jk_tasks.cu:258-261): quartets with estimate above
+ * cutoff_fp32 are evaluated; those not above cutoff_fp64 form the FP32 band and are evaluated in
+ * single precision with FP64 accumulation (jk.py:241-328) for the angular classes that have an FP32
+ * kernel (integral blocks <= 108 elements, one density matrix, hermi == 1), in FP64 otherwise.  With
+ * cutoff_fp64 <= cutoff_fp32 (the default 1e-13 / 1e-13) the build is FP64 only.
+ * Work is enqueued on `stream` (cudaStream_t, NULL = default stream); the call performs one host
+ * synchronisation before the heavy kernels are enqueued (active tile counts), none afterwards;
+ * results are complete when the stream reaches this point. */
 int jqc_get_jk(jqc_engine* eng, const double* dm_dev, int n_dm, int hermi, int with_j, int with_k,
                double omega, double cutoff_fp64, double cutoff_fp32, double* vj_dev, double* vk_dev,
                void* stream);
@@ -110,6 +114,10 @@ int jqc_finalize(jqc_engine* eng, double* vj_dev, double* vk_dev, void* stream);
  * quartets evaluated per class key ((li*5+lj)*5+lk)*5+ll; prim_weighted: the same weighted by
  * npi*npj*npk*npl (for the algorithmic FLOP model of SURVEY 8d); launches: kernels enqueued. */
 int jqc_last_stats(jqc_engine* eng, long long* counts, long long* prim_weighted, int* launches);
+
+/* Mixed-precision accounting of the last build: quartets[0] / quartets[1] = shell quartets evaluated
+ * by the FP64 / FP32 kernels; ms (may be NULL) = their device times when profiling was enabled. */
+int jqc_last_band_stats(jqc_engine* eng, long long* quartets, float* ms);
 
 /* Per-class device time of the last build in ms (625 entries), measured with CUDA events
  * when profiling was enabled before the build (adds synchronisation; off by default). */

@@ -188,6 +188,13 @@ class JKEngine:
         _lib.check(self.L.jqc_last_stats(self.h, counts, pw, ctypes.byref(nl)))
         return np.array(counts[:], dtype=np.int64), np.array(pw[:], dtype=np.int64), int(nl.value)
 
+    def last_band_stats(self):
+        """(quartets evaluated by the FP64 kernels, by the FP32 kernels), (their device ms when profiling)."""
+        n = (ctypes.c_longlong * 2)()
+        ms = (ctypes.c_float * 2)()
+        _lib.check(self.L.jqc_last_band_stats(self.h, n, ms))
+        return (int(n[0]), int(n[1])), (float(ms[0]), float(ms[1]))
+
     def last_class_ms(self):
         ms = (ctypes.c_float * 625)()
         _lib.check(self.L.jqc_last_class_ms(self.h, ms))

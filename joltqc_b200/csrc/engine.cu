@@ -86,7 +86,7 @@ struct QData {                    // per-omega Schwarz data
     std::vector<size_t> h_tab_off;   // npairs: offset (doubles) of each group pair's segment in both tables
 };
 
-struct ChunkRec { int key; long long pw; };   // class key and primitive weight of a launch
+struct ChunkRec { int key; long long pw; bool fp32 = false; };   // class key, primitive weight, precision of a launch
 
 }  // namespace
 
@@ -103,7 +103,7 @@ struct jqc_engine {
     std::map<double, std::unique_ptr<QData>> qcache;
     // per-call scratch
     DevBuf<double> d_dm, d_vjk, d_stage_in, d_stage_j, d_stage_k;
-    DevBuf<float> d_cond, d_logd;
+    DevBuf<float> d_cond, d_logd, d_dm32;
     DevBuf<int> d_logmax, d_nact;
     DevBuf<ushort4> d_queue;
     DevBuf<unsigned> d_counters;
@@ -127,10 +127,13 @@ struct jqc_engine {
     cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr};
     int use_aux = 1;
+    int use_fp32 = 1;
     // state of the last build
     int last_n = 0, last_neff = 0, last_hermi = 1, last_j = 0, last_k = 0, launches = 0;
     bool built = false, profiling = false;
     std::vector<ChunkRec> chunks;
+    long long band_n[2] = {0, 0};   // quartets evaluated by the FP64 / FP32 kernels in the last build
+    float band_ms[2] = {0.f, 0.f};
     std::vector<cudaEvent_t> ev;
     std::vector<float> class_ms = std::vector<float>(625, 0.f);
     int npairs() const { return ngroups * (ngroups + 1) / 2; }
@@ -158,6 +161,7 @@ extern "C" int jqc_engine_create(const jqc_basis_desc* d, int device, jqc_engine
     if (const char* m = getenv("JQC_BWARP")) e->use_bwarp = atoi(m);   // 0 off, 1 measured table, 2 every supported class
     if (const char* m = getenv("JQC_BRICK_ICHUNK")) e->brick_ichunk = std::max(1, atoi(m));
     if (const char* m = getenv("JQC_AUX_STREAMS")) e->use_aux = atoi(m) != 0;
+    if (const char* m = getenv("JQC_FP32")) e->use_fp32 = atoi(m) != 0;     // 0: evaluate the FP32 band in FP64
     if (const char* m = getenv("JQC_QUEUE_CAP")) e->queue_cap = std::min<size_t>(QUEUE_CAP, std::max<size_t>(256, (size_t)atoll(m)));
     if (const char* m = getenv("JQC_KL_CHUNK")) e->kl_chunk_max = std::max(1, atoi(m));
     cudaDeviceProp prop;
@@ -516,6 +520,15 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
         rc = launch_from_mol(e, dm_dev, n_dm, e->d_dm.p + n_dm * nao2, true, st);
         if (rc) return rc;
     }
+    // Mixed precision (jk.py:93-96, 241-328): quartets whose estimate lies in (cutoff_fp32, cutoff_fp64]
+    // go to the FP32 variant of the brick kernel, which reads a float copy of the density.
+    const bool mixed = cutoff_fp64 > cutoff_fp32 && e->use_brick && neff == 1 && !e->small_tiles && e->use_fp32;
+    if (mixed) {
+        CU(e->d_dm32.ensure(std::max<size_t>(nao2, 1)));
+        const unsigned blocks = (unsigned)std::min<size_t>((nao2 + 255) / 256, 65535u * 16);
+        to_float_kernel<<<blocks, 256, 0, st>>>(e->d_dm.p, e->d_dm32.p, nao2);
+        CU(cudaGetLastError());
+    }
     // 2. density pooling on the first n_dm matrices, log, global max
     dm_pool_kernel<<<nbas, 256, nbas * sizeof(float), st>>>(e->d_dm.p, n_dm, nao, nbas, e->d_ao_loc.p, e->d_ao2shell.p,
                                                           e->d_cond.p);
@@ -546,6 +559,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
     double* vj = e->d_vjk.p;
     double* vk = e->d_vjk.p + neff * nao2;
     const float log_cut = (float)std::log(std::min(cutoff_fp32, cutoff_fp64));
+    const float log_cut64 = (float)std::log(cutoff_fp64);
     const int variant = (with_j ? 1 : 0) | (with_k ? 2 : 0);
     e->chunks.clear();
     e->launches = 0;
@@ -599,6 +613,10 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             b.rank = e->rank; b.world = e->world;
             b.work = e->d_counters.p + cid;
             b.qcount = e->d_qcounts.p + cid;
+            b.cutoff_hi = INFINITY;
+            b.dm32 = nullptr;
+            const bool band = mixed && brick_small && brick_shape(li, lj, lk, ll, true).fits;     // this class has an FP32 kernel: split the two bands
+            if (band) b.cutoff = std::max(log_cut, log_cut64);
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (e->profiling) {
                 while (e->ev.size() < nev + 2) { cudaEvent_t x; CU(cudaEventCreate(&x)); e->ev.push_back(x); }
@@ -609,6 +627,26 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
                                fork ? e->aux[n_brick++ % jqc_engine::NAUX] : st));
             if (e->profiling) CU(cudaEventRecord(e1, st));
             e->launches += 1;
+            if (band) {
+                e->chunks.push_back({key, pw});
+                if ((int)e->chunks.size() >= MAX_CHUNKS) return fail(JQC_ENOMEM, "too many task chunks");
+                const int cid2 = (int)e->chunks.size();
+                b.cutoff = log_cut;
+                b.cutoff_hi = log_cut64;
+                b.dm32 = e->d_dm32.p;
+                b.work = e->d_counters.p + cid2;
+                b.qcount = e->d_qcounts.p + cid2;
+                if (e->profiling) {
+                    while (e->ev.size() < nev + 2) { cudaEvent_t x; CU(cudaEventCreate(&x)); e->ev.push_back(x); }
+                    e0 = e->ev[nev++]; e1 = e->ev[nev++];
+                    CU(cudaEventRecord(e0, st));
+                }
+                CU(jk_brick_launch(li, lj, lk, ll, variant | 16, b, e->nsm, fork ? e->aux[n_brick++ % jqc_engine::NAUX] : st));
+                if (e->profiling) CU(cudaEventRecord(e1, st));
+                e->launches += 1;
+                e->chunks.push_back({key, pw, true});
+                continue;
+            }
             e->chunks.push_back({key, pw});
             continue;
         }
@@ -756,15 +794,32 @@ extern "C" int jqc_last_stats(jqc_engine* e, long long* counts, long long* prim_
     if (counts) std::memset(counts, 0, 625 * sizeof(long long));
     if (prim_weighted) std::memset(prim_weighted, 0, 625 * sizeof(long long));
     std::fill(e->class_ms.begin(), e->class_ms.end(), 0.f);
+    e->band_n[0] = e->band_n[1] = 0;
+    e->band_ms[0] = e->band_ms[1] = 0.f;
     for (size_t c = 0; c < h.size(); c++) {
+        e->band_n[e->chunks[c].fp32 ? 1 : 0] += (long long)h[c];
         if (counts) counts[e->chunks[c].key] += h[c];
         if (prim_weighted) prim_weighted[e->chunks[c].key] += (long long)h[c] * e->chunks[c].pw;
         if (e->profiling && e->ev.size() >= 2 * (c + 1)) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, e->ev[2 * c], e->ev[2 * c + 1]) == cudaSuccess) e->class_ms[e->chunks[c].key] += ms;
+            if (cudaEventElapsedTime(&ms, e->ev[2 * c], e->ev[2 * c + 1]) == cudaSuccess) {
+                e->class_ms[e->chunks[c].key] += ms;
+                e->band_ms[e->chunks[c].fp32 ? 1 : 0] += ms;
+            }
         }
     }
     if (launches) *launches = e->launches;
+    return JQC_OK;
+}
+
+extern "C" int jqc_last_band_stats(jqc_engine* e, long long* quartets, float* ms)
+{
+    if (!e || !quartets) return fail(JQC_EINVAL, "null argument");
+    int rc = jqc_last_stats(e, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    quartets[0] = e->band_n[0];
+    quartets[1] = e->band_n[1];
+    if (ms) { ms[0] = e->band_ms[0]; ms[1] = e->band_ms[1]; }
     return JQC_OK;
 }
 

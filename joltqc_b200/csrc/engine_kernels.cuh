@@ -513,6 +513,14 @@ __global__ void q_cond_kernel(const double* __restrict__ basis, const int* __res
 
 // ------------------------------------------------------------------ FP64 peak probe
 // 8 independent DFMA chains per thread, all in registers: sustained FMA-pipe rate.
+// float copy of the kernel-side density for the FP32-band launches (the reference keeps dms_fp32,
+// jqc/pyscf/jk.py:197-199)
+__global__ void to_float_kernel(const double* __restrict__ src, float* __restrict__ dst, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+
 __global__ void fp64_probe_kernel(double* out, int iters, double a, double b)
 {
     double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

@@ -332,16 +332,20 @@ __host__ __device__ constexpr BrickShape brick_shape(int li, int lj, int lk, int
         // 32-bit registers: integrals + g arrays (float) + double accumulators
         const int gs = (li + 1) * (lj + 1) * (lk + 1) * (ll + 1);
         const int live = b.n + 3 * gs + 2 * b.njkl;
-        b.acc_smem = live + 2 * b.nki > 150 && b.nki > 12;
+        b.acc_smem = live + 2 * b.nki > 64 && b.nki > 12;
         b.di_smem = b.nki <= 60;
         const int r = live + (b.acc_smem ? 0 : 2 * b.nki);
-        b.regs = r <= 56 ? 128 : (r <= 100 ? 168 : 255);
+        b.regs = r <= 64 ? 128 : (r <= 140 ? 168 : 255);
         b.rys_bytes = ((size_t)b.nroots * (14 + 2 * b.nroots) * (RYS_NCOEF + 1) * 8 + 15) / 16 * 16;
     }
     b.acc_slots = b.acc_smem ? b.nki : 0;
     b.d_slots = (b.di_smem ? b.nki : 0) + (b.dlk_mode == 1 ? b.njkl : 0);
     b.minb = 65536 / (b.regs * b.nwarps * 32);
     b.smem = b.rys_bytes + (size_t)b.nwarps * 32 * (b.acc_slots * sizeof(double) + b.d_slots * (f32 ? 4 : 8));
+    if (f32 && b.smem * b.minb > 216 * 1024) {      // shared memory, not registers, limits the residency
+        b.minb = (int)(216 * 1024 / b.smem);
+        b.regs = b.minb >= 3 ? 168 : 255;
+    }
     b.fits = b.n <= JQC_SMALL_N && b.smem * b.minb <= 216 * 1024;
     return b;
 }

@@ -93,13 +93,12 @@ static cudaError_t launch_bwarp(const BrickArgs& a_in, int nsm, cudaStream_t st)
     }
 }
 
-template <int LK, int LL, bool DO_J, bool DO_K>
+template <class R, int LK, int LL, bool DO_J, bool DO_K>
 static cudaError_t launch_brick(const BrickArgs& a_in, int nsm, cudaStream_t st)
 {
-    using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
-    using P = BrickPlan<JQC_LI, JQC_LJ, LK, LL>;
+    using P = BrickPlan<R, JQC_LI, JQC_LJ, LK, LL>;
     if constexpr (P::FITS) {
-        auto kern = jk_brick_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K>;
+        auto kern = jk_brick_kernel<R, JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K>;
         static std::atomic<int> cache[JQC_MAX_DEVICES];
         int blocks_per_sm = 1;
         cudaError_t e = blocks_per_sm_cached(cache, kern, P::NWARPS * 32, P::SMEM, &blocks_per_sm);
@@ -188,9 +187,13 @@ template <int LK, int LL>
 static cudaError_t brick_variant(int variant, const BrickArgs& a, int nsm, cudaStream_t st)
 {
     switch (variant) {
-        case 3: return launch_brick<LK, LL, true, true>(a, nsm, st);
-        case 1: return launch_brick<LK, LL, true, false>(a, nsm, st);
-        case 2: return launch_brick<LK, LL, false, true>(a, nsm, st);
+        case 3: return launch_brick<double, LK, LL, true, true>(a, nsm, st);
+        case 1: return launch_brick<double, LK, LL, true, false>(a, nsm, st);
+        case 2: return launch_brick<double, LK, LL, false, true>(a, nsm, st);
+        // FP32-band variant (mixed precision): same classes, float integrals
+        case 19: return launch_brick<float, LK, LL, true, true>(a, nsm, st);
+        case 17: return launch_brick<float, LK, LL, true, false>(a, nsm, st);
+        case 18: return launch_brick<float, LK, LL, false, true>(a, nsm, st);
         case 11: return launch_bwarp<LK, LL, true, true>(a, nsm, st);
         case 9: return launch_bwarp<LK, LL, true, false>(a, nsm, st);
         case 10: return launch_bwarp<LK, LL, false, true>(a, nsm, st);
