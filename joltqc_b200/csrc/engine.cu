@@ -583,17 +583,25 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
         const int key = ((li * 5 + lj) * 5 + lk) * 5 + ll;
         const long long pw = (long long)e->gnp[gi] * e->gnp[gj] * e->gnp[gk] * e->gnp[gl];
         const bool brick_small = brick_shape(li, lj, lk, ll).fits;
-        if (e->use_brick && neff == 1 && !e->small_tiles && (brick_small || (e->use_bwarp && jk_bwarp_supported(li, lj, lk, ll, e->use_bwarp)))) {
-            const int n_kl_pairs = qd->h_pair_off[pkl + 1] - qd->h_pair_off[pkl];
-            const int n_ij_pairs = qd->h_pair_off[pij + 1] - qd->h_pair_off[pij];
+        const bool on_brick = e->use_brick && neff == 1 && !e->small_tiles &&
+                              (brick_small || (e->use_bwarp && jk_bwarp_supported(li, lj, lk, ll, e->use_bwarp)));
+        // FP32 kernel of this class for the mixed-precision band: brick variant up to JQC_SMALL_N
+        // integrals, brick-scheduled multi-lane variant above (up to f shells)
+        const bool f32_brick = brick_shape(li, lj, lk, ll, true).fits;
+        const int band_variant = f32_brick ? 16 : (jk_bwarp_supported(li, lj, lk, ll, 2) ? 24 : 0);
+        const bool band = mixed && band_variant != 0;
+        const int n_kl_pairs = qd->h_pair_off[pkl + 1] - qd->h_pair_off[pkl];
+        const int n_ij_pairs = qd->h_pair_off[pij + 1] - qd->h_pair_off[pij];
+        BrickArgs b;
+        if (on_brick || band) {
             if (n_kl_pairs == 0 || n_ij_pairs == 0) continue;
-            if ((int)e->chunks.size() >= MAX_CHUNKS) return fail(JQC_ENOMEM, "too many task chunks");
-            const int cid = (int)e->chunks.size();
-            BrickArgs b;
             b.nao = nao; b.nbas = nbas;
             b.npi = e->gnp[gi]; b.npj = e->gnp[gj]; b.npk = e->gnp[gk]; b.npl = e->gnp[gl];
             b.basis = e->d_basis.p; b.dm = e->d_dm.p; b.vj = vj; b.vk = vk; b.omega = omega;
-            b.logd = e->d_logd.p; b.log_max_ordered = e->d_logmax.p; b.cutoff = log_cut;
+            b.logd = e->d_logd.p; b.log_max_ordered = e->d_logmax.p;
+            b.cutoff = band ? std::max(log_cut, log_cut64) : log_cut;
+            b.cutoff_hi = INFINITY;
+            b.dm32 = nullptr;
             b.kl = qd->kl.p + qd->h_pair_off[pkl];
             b.kl_q = qd->kl_q.p + qd->h_pair_off[pkl];
             b.kl_tq = qd->kl_tq.p + qd->h_pair_off[pkl];
@@ -611,43 +619,40 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             b.ichunk_req = e->brick_ichunk;
             b.n_blk = b.ichunk = b.n_ichunk = b.jsplit = 0;      // set by the launcher (brick_decompose)
             b.rank = e->rank; b.world = e->world;
+        }
+        // one launch of the brick family (FP64 share, or the FP32 band) with its own task counter
+        auto brick_family_launch = [&](int var, bool fp32) -> int {
+            if ((int)e->chunks.size() >= MAX_CHUNKS) return fail(JQC_ENOMEM, "too many task chunks");
+            const int cid = (int)e->chunks.size();
             b.work = e->d_counters.p + cid;
             b.qcount = e->d_qcounts.p + cid;
-            b.cutoff_hi = INFINITY;
-            b.dm32 = nullptr;
-            const bool band = mixed && brick_small && brick_shape(li, lj, lk, ll, true).fits;     // this class has an FP32 kernel: split the two bands
-            if (band) b.cutoff = std::max(log_cut, log_cut64);
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (e->profiling) {
                 while (e->ev.size() < nev + 2) { cudaEvent_t x; CU(cudaEventCreate(&x)); e->ev.push_back(x); }
                 e0 = e->ev[nev++]; e1 = e->ev[nev++];
                 CU(cudaEventRecord(e0, st));
             }
-            CU(jk_brick_launch(li, lj, lk, ll, variant | (brick_small ? 0 : 8), b, e->nsm,
-                               fork ? e->aux[n_brick++ % jqc_engine::NAUX] : st));
+            CU(jk_brick_launch(li, lj, lk, ll, var, b, e->nsm, fork ? e->aux[n_brick++ % jqc_engine::NAUX] : st));
             if (e->profiling) CU(cudaEventRecord(e1, st));
             e->launches += 1;
-            if (band) {
-                e->chunks.push_back({key, pw});
-                if ((int)e->chunks.size() >= MAX_CHUNKS) return fail(JQC_ENOMEM, "too many task chunks");
-                const int cid2 = (int)e->chunks.size();
-                b.cutoff = log_cut;
-                b.cutoff_hi = log_cut64;
-                b.dm32 = e->d_dm32.p;
-                b.work = e->d_counters.p + cid2;
-                b.qcount = e->d_qcounts.p + cid2;
-                if (e->profiling) {
-                    while (e->ev.size() < nev + 2) { cudaEvent_t x; CU(cudaEventCreate(&x)); e->ev.push_back(x); }
-                    e0 = e->ev[nev++]; e1 = e->ev[nev++];
-                    CU(cudaEventRecord(e0, st));
-                }
-                CU(jk_brick_launch(li, lj, lk, ll, variant | 16, b, e->nsm, fork ? e->aux[n_brick++ % jqc_engine::NAUX] : st));
-                if (e->profiling) CU(cudaEventRecord(e1, st));
-                e->launches += 1;
-                e->chunks.push_back({key, pw, true});
-                continue;
-            }
-            e->chunks.push_back({key, pw});
+            e->chunks.push_back({key, pw, fp32});
+            return JQC_OK;
+        };
+        if (band) {
+            // quartets with cutoff_fp32 < estimate <= cutoff_fp64 (screen_jk_tasks.cu:258-261)
+            const float lo = b.cutoff;
+            b.cutoff = log_cut;
+            b.cutoff_hi = log_cut64;
+            b.dm32 = e->d_dm32.p;
+            rc = brick_family_launch(variant | band_variant, true);
+            if (rc) return rc;
+            b.cutoff = lo;
+            b.cutoff_hi = INFINITY;
+            b.dm32 = nullptr;
+        }
+        if (on_brick) {
+            rc = brick_family_launch(variant | (brick_small ? 0 : 8), false);
+            if (rc) return rc;
             continue;
         }
         // quartet-list path: this rank owns list entries rank, rank + world, ... of the ij tile list
@@ -681,7 +686,7 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             s.kl_count = std::min(kl_chunk, n_kl - kl0);
             s.rank = e->rank;
             s.world = e->world;
-            s.cutoff = log_cut;
+            s.cutoff = band ? std::max(log_cut, log_cut64) : log_cut;
             s.do_j = with_j;
             s.do_k = with_k;
             s.queue = e->d_queue.p;

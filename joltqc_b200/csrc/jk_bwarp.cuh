@@ -20,12 +20,15 @@
 
 namespace jqc {
 
-template <int LI, int LJ, int LK, int LL>
+template <class R, int LI, int LJ, int LK, int LL>
 struct BWarpPlan {
     using S = QuartetShape<LI, LJ, LK, LL>;
+    static constexpr bool F32 = sizeof(R) == 4;
     using W = WarpPlan<LI, LJ, LK, LL>;
     static constexpr int T = W::T, QPW = W::QPW, NKLP = W::NKLP, NKL = W::NKL, NIJ = W::NIJ, NPASS = W::NPASS, NJC = W::NJC;
-    static constexpr int PASS_ACC = W::PASS_ACC, REGS = W::REGS;
+    // FP32-band variant: accumulators, g arrays and density blocks are float (half the registers and
+    // shared memory per group), which buys residency: 168 registers -> 12 warps per SM
+    static constexpr int PASS_ACC = W::PASS_ACC, REGS = F32 ? (W::REGS > 168 ? 168 : W::REGS) : W::REGS;
     static constexpr int IS = W::IS, G_ALL = W::G_ALL;
     // per-group shared memory (doubles).  With a single bra pass the K_jk / K_jl staging area
     // aliases the g arrays (dead once the products of the quartet are done).
@@ -52,11 +55,11 @@ struct BWarpPlan {
     // per-warp shared memory: D_ji + the groups
     static constexpr int OFF_DJI = 0;
     static constexpr int OFF_GROUPS = (OFF_DJI + NIJ + 15) / 16 * 16;
-    static constexpr size_t WARP_DOUBLES = ((size_t)OFF_GROUPS + (size_t)QPW * PER_GROUP + 3) / 4 * 4;
-    static constexpr size_t WARP_BYTES = WARP_DOUBLES * sizeof(double);
+    static constexpr size_t WARP_DOUBLES = ((size_t)OFF_GROUPS + (size_t)QPW * PER_GROUP + 3) / 4 * 4;   // elements of R
+    static constexpr size_t WARP_BYTES = WARP_DOUBLES * sizeof(R);
     static constexpr int nwarps()
     {
-        int n = (int)(56 * 1024 / WARP_BYTES);
+        int n = (int)((F32 ? 36 : 56) * 1024 / WARP_BYTES);
         return n > 4 ? 4 : (n < 1 ? 1 : n);
     }
     static constexpr int NWARPS = nwarps();
@@ -70,42 +73,48 @@ struct BWarpPlan {
         _Pragma("unroll") for (int m = 0; m < ((NR) * (NC) + T - 1) / T; m++) {                    \
             const int e_ = t + m * T;                                                              \
             if (e_ < (NR) * (NC)) { const int r_ = e_ / (NC), c_ = e_ - r_ * (NC);                 \
-                (DST)[e_] = __ldg(dm + (size_t)((R0) + r_) * nao + (C0) + c_); }                   \
+                (DST)[e_] = ldd((size_t)((R0) + r_) * nao + (C0) + c_); }                   \
         }                                                                                          \
     }
 
-template <int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 65536 / (BWarpPlan<LI, LJ, LK, LL>::REGS * NWARPS * 32))
+template <class R, int LI, int LJ, int LK, int LL, bool DO_J, bool DO_K, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 65536 / (BWarpPlan<R, LI, LJ, LK, LL>::REGS * NWARPS * 32))
 jk_bwarp_kernel(const BrickArgs a)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
-    using P = BWarpPlan<LI, LJ, LK, LL>;
+    using P = BWarpPlan<R, LI, LJ, LK, LL>;
+    constexpr bool F32 = P::F32;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL;
     constexpr int NROOTS = S::NROOTS, GS = P::IS, DJ = S::DJ, DK = P::W::DKP, DL = P::W::DLP;
     constexpr int T = P::T, QPW = P::QPW, NKLP = P::NKLP, NKL = P::NKL, NPASS = P::NPASS, NJC = P::NJC, NIJ = P::NIJ;
     constexpr unsigned FULL = 0xffffffffu;
 
-    extern __shared__ double smem[];
+    extern __shared__ double smem_raw[];
+    R* __restrict__ smem = reinterpret_cast<R*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / T, t = lane - grp * T;
     const bool lane_ok = grp < QPW;
-    double* __restrict__ sw = smem + (size_t)warp * P::WARP_DOUBLES;
-    double* __restrict__ s_dji = sw + P::OFF_DJI;
-    double* __restrict__ sg = sw + P::OFF_GROUPS + (size_t)(lane_ok ? grp : 0) * P::PER_GROUP;
-    double* __restrict__ s_rw = sg + P::OFF_RW;
-    double* __restrict__ s_g = sg + P::OFF_G;
-    double* __restrict__ s_djl = sg + P::OFF_DJL;
-    double* __restrict__ s_djk = sg + P::OFF_DJK;
-    double* __restrict__ s_dil = sg + P::OFF_DIL;
-    double* __restrict__ s_dik = sg + P::OFF_DIK;
-    double* __restrict__ s_stjk = sg + P::OFF_STJK;
-    double* __restrict__ s_stjl = sg + P::OFF_STJL;
-    double* __restrict__ s_kp = sg + P::OFF_KP + t;      // element x of this lane at s_kp[x * T]
+    R* __restrict__ sw = smem + (size_t)warp * P::WARP_DOUBLES;
+    R* __restrict__ s_dji = sw + P::OFF_DJI;
+    R* __restrict__ sg = sw + P::OFF_GROUPS + (size_t)(lane_ok ? grp : 0) * P::PER_GROUP;
+    R* __restrict__ s_rw = sg + P::OFF_RW;
+    R* __restrict__ s_g = sg + P::OFF_G;
+    R* __restrict__ s_djl = sg + P::OFF_DJL;
+    R* __restrict__ s_djk = sg + P::OFF_DJK;
+    R* __restrict__ s_dil = sg + P::OFF_DIL;
+    R* __restrict__ s_dik = sg + P::OFF_DIK;
+    R* __restrict__ s_stjk = sg + P::OFF_STJK;
+    R* __restrict__ s_stjl = sg + P::OFF_STJL;
+    R* __restrict__ s_kp = sg + P::OFF_KP + t;      // element x of this lane at s_kp[x * T]
 #define KP_IK(s, i) s_kp[((s) * NFI + (i)) * T]
 #define KP_IL(s, i) s_kp[((NKLP + (s)) * NFI + (i)) * T]
 
     const int nao = a.nao, nbas = a.nbas;
-    const double* __restrict__ dm = a.dm;
+    // density elements in the precision of this launch
+    auto ldd = [&](size_t off) -> R {
+        if constexpr (F32) return __ldg(a.dm32 + off);
+        else return __ldg(a.dm + off);
+    };
     const float log_max = ordered_to_float(*a.log_max_ordered);
     const float dmaxf = fmaxf(log_max, -36.8f);
     const double paircut = log(1e-13) - (double)log_max;
@@ -157,15 +166,16 @@ jk_bwarp_kernel(const BrickArgs a)
         const double4 rk = *reinterpret_cast<const double4*>(bk);
         const double4 rl = *reinterpret_cast<const double4*>(bl);
         const int k0 = (int)rk.w, l0 = (int)rl.w;
-        const double rlrk[3] = {rl.x - rk.x, rl.y - rk.y, rl.z - rk.z};
+        const R rlrk[3] = {(R)(rl.x - rk.x), (R)(rl.y - rk.y), (R)(rl.z - rk.z)};
         const float d_kl = a.logd[(size_t)ksh * nbas + lsh];
         const double* __restrict__ ket = a.ket_tab + (size_t)pp * npkl * 8;
 
-        double jkl[NKLP], dlk[NKLP];
+        double jkl[NKLP];
+        R dlk[NKLP];
 #pragma unroll
         for (int s = 0; s < NKLP; s++) {
             jkl[s] = 0.0;
-            dlk[s] = pv[s] ? __ldg(dm + (size_t)(l0 + pl[s]) * nao + k0 + pk[s]) : 0.0;
+            dlk[s] = pv[s] ? ldd((size_t)(l0 + pl[s]) * nao + k0 + pk[s]) : R(0);
         }
         bool touched_kl = false;
 
@@ -195,7 +205,7 @@ jk_bwarp_kernel(const BrickArgs a)
                     JQC_BW_STAGE(s_dil, NFI, NFL, i0, l0)
                     JQC_BW_STAGE(s_dik, NFI, NFK, i0, k0)
 #pragma unroll
-                    for (int x = 0; x < 2 * NKLP * NFI; x++) s_kp[x * T] = 0.0;
+                    for (int x = 0; x < 2 * NKLP * NFI; x++) s_kp[x * T] = R(0);
                 }
             }
             __syncwarp();
@@ -221,7 +231,8 @@ jk_bwarp_kernel(const BrickArgs a)
                         d_large = fmaxf(d_large, a.logd[(size_t)ish * nbas + jsh]);
                         d_large = fmaxf(d_large, d_kl);
                     }
-                    live = q_ijkl + d_large > a.cutoff;
+                    const float dq = q_ijkl + d_large;
+                    live = dq > a.cutoff && !(dq > a.cutoff_hi);     // precision band of this launch
                 }
                 const unsigned m = __ballot_sync(FULL, live && t == 0);
                 if (m == 0) continue;
@@ -231,11 +242,11 @@ jk_bwarp_kernel(const BrickArgs a)
                 const double* __restrict__ bj = a.basis + jsh * BASIS_STRIDE;
                 const double4 rj = *reinterpret_cast<const double4*>(bj);
                 const int j0 = (int)rj.w;
-                double fac = live ? PI_FAC : 0.0;
-                if (ish == jsh) fac *= 0.5;
-                if (ksh == lsh) fac *= 0.5;
-                if (ish == ksh && jsh == lsh) fac *= 0.5;
-                const double rjri[3] = {rj.x - ri.x, rj.y - ri.y, rj.z - ri.z};
+                R fac = live ? R(PI_FAC) : R(0);
+                if (ish == jsh) fac *= R(0.5);
+                if (ksh == lsh) fac *= R(0.5);
+                if (ish == ksh && jsh == lsh) fac *= R(0.5);
+                const R rjri[3] = {(R)(rj.x - ri.x), (R)(rj.y - ri.y), (R)(rj.z - ri.z)};
 
                 // per-step staging: D_ji (one copy per warp), D_jl / D_jk (per group)
                 const double* __restrict__ bra = a.bra_tab + (size_t)(e - a.j_base) * npij * 8;
@@ -243,7 +254,7 @@ jk_bwarp_kernel(const BrickArgs a)
 #pragma unroll
                 for (int m2 = 0; m2 < (NIJ + 31) / 32; m2++) {
                     const int x = lane + m2 * 32;
-                    if (x < NIJ) { const int jj = x / NFI, ii = x - jj * NFI; s_dji[x] = __ldg(dm + (size_t)(j0 + jj) * nao + i0 + ii); }
+                    if (x < NIJ) { const int jj = x / NFI, ii = x - jj * NFI; s_dji[x] = ldd((size_t)(j0 + jj) * nao + i0 + ii); }
                 }
                 if (lane_ok) {
                     if constexpr (DO_K) {
@@ -256,46 +267,46 @@ jk_bwarp_kernel(const BrickArgs a)
 #pragma unroll
                 for (int pass = 0; pass < NPASS; pass++) {
                     const int jc0 = pass * NJC;
-                    double acc[NKLP][NJC * NFI];
+                    R acc[NKLP][NJC * NFI];
 #pragma unroll
                     for (int s = 0; s < NKLP; s++)
 #pragma unroll
-                        for (int x = 0; x < NJC * NFI; x++) acc[s][x] = 0.0;
+                        for (int x = 0; x < NJC * NFI; x++) acc[s][x] = R(0);
 
 #pragma unroll 1
                     for (int klp = 0; klp < npkl; klp++) {
                         const double4 kt0 = *reinterpret_cast<const double4*>(ket + klp * 8);
                         const double4 kt1 = *reinterpret_cast<const double4*>(ket + klp * 8 + 4);
-                        const double akl = kt0.x, inv_akl = kt0.y, al_akl = kt0.z, ckcl = kt0.w;
+                        const R akl = (R)kt0.x, inv_akl = (R)kt0.y, al_akl = (R)kt0.z, ckcl = (R)kt0.w;
                         const double qx = kt1.x, qy = kt1.y, qz = kt1.z;
 #pragma unroll 1
                         for (int ipj = 0; ipj < npij; ipj++) {
                             __syncwarp();   // staging visible; previous product phase has finished reading g
                             const double4 b0 = *reinterpret_cast<const double4*>(bra + ipj * 8);
                             const double4 b1 = *reinterpret_cast<const double4*>(bra + ipj * 8 + 4);
-                            const double aij = b0.x, inv_aij = b0.y, aj_aij = b0.z;
-                            const double cicj = fac * b0.w;
-                            const double Rpq[3] = {b1.x - qx, b1.y - qy, b1.z - qz};
-                            const double rr = Rpq[0] * Rpq[0] + Rpq[1] * Rpq[1] + Rpq[2] * Rpq[2];
-                            const double inv_aijkl = 1.0 / (aij + akl);
-                            const double theta = aij * akl * inv_aijkl;
-                            const double gy0 = cicj * inv_aij * inv_akl * sqrt(inv_aijkl);
-                            double theta_fac = 1.0, sqrt_theta_fac = 1.0;
+                            const R aij = (R)b0.x, inv_aij = (R)b0.y, aj_aij = (R)b0.z;
+                            const R cicj = fac * (R)b0.w;
+                            const R Rpq[3] = {(R)(b1.x - qx), (R)(b1.y - qy), (R)(b1.z - qz)};
+                            const R rr = Rpq[0] * Rpq[0] + Rpq[1] * Rpq[1] + Rpq[2] * Rpq[2];
+                            const R inv_aijkl = R(1) / (aij + akl);
+                            const R theta = aij * akl * inv_aijkl;
+                            const R gy0 = cicj * inv_aij * inv_akl * sqrt(inv_aijkl);
+                            R theta_fac = R(1), sqrt_theta_fac = R(1);
                             if (a.omega > 0.0) {
-                                const double o2 = a.omega * a.omega;
+                                const R o2 = (R)(a.omega * a.omega);
                                 theta_fac = o2 / (o2 + theta);
                                 sqrt_theta_fac = sqrt(theta_fac);
                             }
-                            const double x = rr * theta * theta_fac;
+                            const R x = rr * theta * theta_fac;
                             // with one primitive quartet the g arrays of pass 0 stay valid in later passes
                             const bool reuse_g = (NPASS > 1) && pass > 0 && single_prim;
                             if (lane_ok && !reuse_g) {
 #pragma unroll 1
                                 for (int r = t; r < NROOTS; r += T) {
-                                    double rt, wt;
-                                    rys_root_one<NROOTS>(x, r, rt, wt);
-                                    s_rw[2 * r] = rt * theta_fac;
-                                    s_rw[2 * r + 1] = wt * sqrt_theta_fac;
+                                    double rt, wt;      // (the root finder stays FP64: 2 series per lane, off the hot loop)
+                                    rys_root_one<NROOTS>((double)x, r, rt, wt);
+                                    s_rw[2 * r] = (R)rt * theta_fac;
+                                    s_rw[2 * r + 1] = (R)wt * sqrt_theta_fac;
                                 }
                             }
                             __syncwarp();
@@ -303,18 +314,18 @@ jk_bwarp_kernel(const BrickArgs a)
 #pragma unroll 1
                                 for (int item = t; item < 3 * NROOTS; item += T) {
                                     const int r = item / 3, d = item - 3 * r;
-                                    const double rt = s_rw[2 * r], wt = s_rw[2 * r + 1];
-                                    const double rt_aa = rt * inv_aijkl;
-                                    const double rt_aij = rt_aa * akl, rt_akl = rt_aa * aij;
-                                    const double b10 = 0.5 * inv_aij * (1.0 - rt_aij);
-                                    const double b01 = 0.5 * inv_akl * (1.0 - rt_akl);
-                                    const double b00 = 0.5 * rt_aa;
-                                    const double ab = d == 0 ? rjri[0] : (d == 1 ? rjri[1] : rjri[2]);
-                                    const double cd = d == 0 ? rlrk[0] : (d == 1 ? rlrk[1] : rlrk[2]);
-                                    const double pq = d == 0 ? Rpq[0] : (d == 1 ? Rpq[1] : Rpq[2]);
-                                    const double seed = d == 0 ? ckcl : (d == 1 ? gy0 : wt);
-                                    const double c0 = fma(ab, aj_aij, -rt_aij * pq);
-                                    const double cp = fma(cd, al_akl, rt_akl * pq);
+                                    const R rt = s_rw[2 * r], wt = s_rw[2 * r + 1];
+                                    const R rt_aa = rt * inv_aijkl;
+                                    const R rt_aij = rt_aa * akl, rt_akl = rt_aa * aij;
+                                    const R b10 = R(0.5) * inv_aij * (R(1) - rt_aij);
+                                    const R b01 = R(0.5) * inv_akl * (R(1) - rt_akl);
+                                    const R b00 = R(0.5) * rt_aa;
+                                    const R ab = d == 0 ? rjri[0] : (d == 1 ? rjri[1] : rjri[2]);
+                                    const R cd = d == 0 ? rlrk[0] : (d == 1 ? rlrk[1] : rlrk[2]);
+                                    const R pq = d == 0 ? Rpq[0] : (d == 1 ? Rpq[1] : Rpq[2]);
+                                    const R seed = d == 0 ? ckcl : (d == 1 ? gy0 : wt);
+                                    const R c0 = fma(ab, aj_aij, -rt_aij * pq);
+                                    const R cp = fma(cd, al_akl, rt_akl * pq);
                                     fill_g_dir_regs<LI, LJ, LK, LL>(s_g + (size_t)item * GS, seed, c0, cp, b10, b01, b00, ab, cd);
                                 }
                             }
@@ -325,10 +336,10 @@ jk_bwarp_kernel(const BrickArgs a)
                                     if (!pv[s]) continue;
 #pragma unroll 1
                                     for (int r = 0; r < NROOTS; r++) {
-                                        const double* __restrict__ g = s_g + r * 3 * GS;
-                                        const double* __restrict__ gx = g + pox[s];
-                                        const double* __restrict__ gy = g + poy[s];
-                                        const double* __restrict__ gz = g + poz[s];
+                                        const R* __restrict__ g = s_g + r * 3 * GS;
+                                        const R* __restrict__ gx = g + pox[s];
+                                        const R* __restrict__ gy = g + poy[s];
+                                        const R* __restrict__ gz = g + poz[s];
 #pragma unroll
                                         for (int jj = 0; jj < NJC; jj++)
 #pragma unroll
@@ -351,12 +362,12 @@ jk_bwarp_kernel(const BrickArgs a)
                         for (int s = 0; s < NKLP; s++) {
                             if (!pv[s]) continue;
                             // J_kl += sum_ij (ij|kl) D[j,i]: stationary in registers for the whole task
-                            double sj = 0.0;
+                            R sj = R(0);
 #pragma unroll
                             for (int jj = 0; jj < NJC; jj++)
 #pragma unroll
                                 for (int i = 0; i < NFI; i++) sj = fma(acc[s][jj * NFI + i], s_dji[(jc0 + jj) * NFI + i], sj);
-                            jkl[s] += sj;
+                            jkl[s] += (double)sj;
                         }
                         // J_ij: same addresses for all groups of the warp -> reduce-scatter over the 32 lanes,
                         // in chunks of 16 elements to bound the live registers
@@ -364,10 +375,10 @@ jk_bwarp_kernel(const BrickArgs a)
 #pragma unroll
                         for (int c0 = 0; c0 < NV; c0 += CH) {
                             constexpr int dummy = 0; (void)dummy;
-                            double vij[CH];
+                            R vij[CH];
 #pragma unroll
                             for (int x = 0; x < CH; x++) {
-                                double v = 0.0;
+                                R v = R(0);
                                 if (c0 + x < NV) {
 #pragma unroll
                                     for (int s = 0; s < NKLP; s++) v = fma(acc[s][(c0 + x) < NV ? (c0 + x) : 0], dlk[s], v);
@@ -378,7 +389,7 @@ jk_bwarp_kernel(const BrickArgs a)
                             WarpReduceScatter<CH, 16>::run(vij, lane, idx, cnt);
                             if (cnt > 0 && c0 + idx < NV) {
                                 const int jj = (c0 + idx) / NFI, i = (c0 + idx) - jj * NFI;
-                                atomicAdd(a.vj + (size_t)(j0 + jc0 + jj) * nao + i0 + i, vij[0]);
+                                atomicAdd(a.vj + (size_t)(j0 + jc0 + jj) * nao + i0 + i, (double)vij[0]);
                             }
                         }
                     }
@@ -388,7 +399,7 @@ jk_bwarp_kernel(const BrickArgs a)
                             for (int s = 0; s < NKLP; s++) {
                                 if (!pv[s]) continue;
                                 const int kc = pk[s], lc = pl[s], pr = lc * NFK + kc;
-                                double djl[NJC], djk[NJC], dil[NFI], dik[NFI];
+                                R djl[NJC], djk[NJC], dil[NFI], dik[NFI];
 #pragma unroll
                                 for (int jj = 0; jj < NJC; jj++) {
                                     djl[jj] = s_djl[(jc0 + jj) * NFL + lc];
@@ -402,7 +413,7 @@ jk_bwarp_kernel(const BrickArgs a)
                                 // K_ik / K_il partials of this lane's pair: stationary over the j loop
 #pragma unroll
                                 for (int i = 0; i < NFI; i++) {
-                                    double va = 0.0, vb = 0.0;
+                                    R va = R(0), vb = R(0);
 #pragma unroll
                                     for (int jj = 0; jj < NJC; jj++) {
                                         va = fma(acc[s][jj * NFI + i], djl[jj], va);
@@ -414,7 +425,7 @@ jk_bwarp_kernel(const BrickArgs a)
                                 // K_jk / K_jl partials: staged, combined over the group's lanes below
 #pragma unroll
                                 for (int jj = 0; jj < NJC; jj++) {
-                                    double vc = 0.0, vd = 0.0;
+                                    R vc = R(0), vd = R(0);
 #pragma unroll
                                     for (int i = 0; i < NFI; i++) {
                                         vc = fma(acc[s][jj * NFI + i], dil[i], vc);
@@ -436,10 +447,10 @@ jk_bwarp_kernel(const BrickArgs a)
                             const int x = t + m2 * T;
                             if (x < NFJ * NFK) {
                                 const int r = x / NFK, c = x - r * NFK;
-                                double v = 0.0;
+                                R v = R(0);
 #pragma unroll
                                 for (int l = 0; l < NFL; l++) v += s_stjk[(l * NFK + c) * NFJ + r];
-                                atomicAdd(a.vk + (size_t)(j0 + r) * nao + k0 + c, v);
+                                atomicAdd(a.vk + (size_t)(j0 + r) * nao + k0 + c, (double)v);
                             }
                         }
 #pragma unroll
@@ -447,10 +458,10 @@ jk_bwarp_kernel(const BrickArgs a)
                             const int x = t + m2 * T;
                             if (x < NFJ * NFL) {
                                 const int r = x / NFL, c = x - r * NFL;
-                                double v = 0.0;
+                                R v = R(0);
 #pragma unroll
                                 for (int k = 0; k < NFK; k++) v += s_stjl[(c * NFK + k) * NFJ + r];
-                                atomicAdd(a.vk + (size_t)(j0 + r) * nao + l0 + c, v);
+                                atomicAdd(a.vk + (size_t)(j0 + r) * nao + l0 + c, (double)v);
                             }
                         }
                     }
@@ -464,8 +475,8 @@ jk_bwarp_kernel(const BrickArgs a)
                         if (!pv[s]) continue;
 #pragma unroll
                         for (int i = 0; i < NFI; i++) {
-                            atomicAdd(a.vk + (size_t)(i0 + i) * nao + k0 + pk[s], KP_IK(s, i));
-                            atomicAdd(a.vk + (size_t)(i0 + i) * nao + l0 + pl[s], KP_IL(s, i));
+                            atomicAdd(a.vk + (size_t)(i0 + i) * nao + k0 + pk[s], (double)KP_IK(s, i));
+                            atomicAdd(a.vk + (size_t)(i0 + i) * nao + l0 + pl[s], (double)KP_IL(s, i));
                         }
                     }
                 }

@@ -69,13 +69,13 @@ static cudaError_t launch_warp(const JKArgs& a, int nsm, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int LK, int LL, bool DO_J, bool DO_K>
+template <class R, int LK, int LL, bool DO_J, bool DO_K>
 static cudaError_t launch_bwarp(const BrickArgs& a_in, int nsm, cudaStream_t st)
 {
     using S = QuartetShape<JQC_LI, JQC_LJ, LK, LL>;
-    using P = BWarpPlan<JQC_LI, JQC_LJ, LK, LL>;
+    using P = BWarpPlan<R, JQC_LI, JQC_LJ, LK, LL>;
     if constexpr (S::N > JQC_SMALL_N && P::FITS && JQC_LI <= 3) {
-        auto kern = jk_bwarp_kernel<JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, P::NWARPS>;
+        auto kern = jk_bwarp_kernel<R, JQC_LI, JQC_LJ, LK, LL, DO_J, DO_K, P::NWARPS>;
         static std::atomic<int> cache[JQC_MAX_DEVICES];
         int blocks_per_sm = 1;
         cudaError_t e = blocks_per_sm_cached(cache, kern, P::NWARPS * 32, P::SMEM, &blocks_per_sm);
@@ -194,9 +194,12 @@ static cudaError_t brick_variant(int variant, const BrickArgs& a, int nsm, cudaS
         case 19: return launch_brick<float, LK, LL, true, true>(a, nsm, st);
         case 17: return launch_brick<float, LK, LL, true, false>(a, nsm, st);
         case 18: return launch_brick<float, LK, LL, false, true>(a, nsm, st);
-        case 11: return launch_bwarp<LK, LL, true, true>(a, nsm, st);
-        case 9: return launch_bwarp<LK, LL, true, false>(a, nsm, st);
-        case 10: return launch_bwarp<LK, LL, false, true>(a, nsm, st);
+        case 11: return launch_bwarp<double, LK, LL, true, true>(a, nsm, st);
+        case 9: return launch_bwarp<double, LK, LL, true, false>(a, nsm, st);
+        case 10: return launch_bwarp<double, LK, LL, false, true>(a, nsm, st);
+        case 27: return launch_bwarp<float, LK, LL, true, true>(a, nsm, st);
+        case 25: return launch_bwarp<float, LK, LL, true, false>(a, nsm, st);
+        case 26: return launch_bwarp<float, LK, LL, false, true>(a, nsm, st);
     }
     return cudaErrorInvalidValue;
 }

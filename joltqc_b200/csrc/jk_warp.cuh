@@ -72,18 +72,17 @@ __device__ __forceinline__ void rys_root_one_smem(double x, int i, double& root,
 // is stored once; the (k -> l) HRR then reads each (i,j) column back once.  Shared-memory traffic
 // is ~1 access per recurrence step instead of 3 for the in-place form below, and the dependent
 // chains run at register latency.
-template <int LI, int LJ, int LK, int LL>
-__device__ __forceinline__ void fill_g_dir_regs(double* __restrict__ gd, const double seed, const double c0, const double cp,
-                                                const double b10, const double b01, const double b00, const double ab,
-                                                const double cd)
+template <int LI, int LJ, int LK, int LL, class R>
+__device__ __forceinline__ void fill_g_dir_regs(R* __restrict__ gd, const R seed, const R c0, const R cp, const R b10,
+                                                const R b01, const R b00, const R ab, const R cd)
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     constexpr int DJ = S::DJ, DK = WarpLayout<LI, LJ, LK, LL>::DKP, DL = DK * (LK + 1), LIJ = S::LIJ, LKL = S::LKL;
-    double prev[LIJ + 1], cur[LIJ + 1];
+    R prev[LIJ + 1], cur[LIJ + 1];
 #pragma unroll
     for (int k = 0; k <= LKL; k++) {
         // row k of the TRR table g(i, 0 | k, 0)
-        double row[LIJ + 1];
+        R row[LIJ + 1];
         if (k == 0) {
             row[0] = seed;
             if constexpr (LIJ > 0) row[1] = c0 * seed;
@@ -92,7 +91,7 @@ __device__ __forceinline__ void fill_g_dir_regs(double* __restrict__ gd, const d
         } else {
 #pragma unroll
             for (int i = 0; i <= LIJ; i++) {
-                double v = cp * cur[i];
+                R v = cp * cur[i];
                 if (k > 1) v = fma((k - 1) * b01, prev[i], v);
                 if (i > 0) v = fma(i * b00, cur[i - 1], v);
                 row[i] = v;
@@ -118,7 +117,7 @@ __device__ __forceinline__ void fill_g_dir_regs(double* __restrict__ gd, const d
 #pragma unroll
         for (int i = 0; i <= LI; i++) {
             const int ij = i + j * DJ;
-            double v[LKL + 1];
+            R v[LKL + 1];
 #pragma unroll
             for (int k = 0; k <= LKL; k++) v[k] = gd[ij + k * DK];
 #pragma unroll

@@ -52,7 +52,7 @@ def test_jk_mixed_precision_h2o(torch_cuda):
 def test_band_split_keeps_the_quartet_set(torch_cuda, with_j, with_k):
     """Every quartet above cutoff_fp32 is evaluated exactly once: per-class counts of the mixed build
     equal those of the FP64 build and of the oracle; the FP64 kernels see exactly the quartets above
-    cutoff_fp64 for the classes that have an FP32 kernel."""
+    cutoff_fp64 for the classes that have an FP32 kernel (all classes up to f shells)."""
     mol, lay = make(benzene(), "def2-tzvp")
     dm = random_dm(mol.nao, 3) * 0.02
     eng = lay.engine()
@@ -69,17 +69,13 @@ def test_band_split_keeps_the_quartet_set(torch_cuda, with_j, with_k):
     orc = OracleJK(lay)
     orc.get_jk(dm, 1, with_j, with_k, None, 1e-13)
     assert np.array_equal(c_mixed, orc.last_counts)
-    # quartets above cutoff_fp64: the FP64 share of the mixed build can only exceed it by the classes
-    # without an FP32 kernel (> 108 integrals), whose band is evaluated in FP64
+    # the FP64 kernels see exactly the quartets above cutoff_fp64, except in classes without an FP32
+    # kernel (g shells with more than 108 integrals), whose band is evaluated in FP64
     orc.get_jk(dm, 1, with_j, with_k, None, 1e-7)
     hi = orc.last_counts
     nf = lambda l: (l + 1) * (l + 2) // 2
-    small = np.array([nf(k // 125) * nf(k // 25 % 5) * nf(k // 5 % 5) * nf(k % 5) <= 108 for k in range(625)])
-    # (30|30) and (40|20) have <= 108 integrals but their FP64 brick kernel does not fit the shared-memory
-    # budget (jk_brick.cuh: brick_shape().fits); they stay on the quartet-list FP64 kernels, band included
-    small[(3 * 5 + 0) * 25 + 3 * 5 + 0] = False
-    small[(4 * 5 + 0) * 25 + 2 * 5 + 0] = False
-    assert b64 == hi[small].sum() + c_fp64[~small].sum()
+    capable = np.array([nf(k // 125) * nf(k // 25 % 5) * nf(k // 5 % 5) * nf(k % 5) <= 108 or k // 125 <= 3 for k in range(625)])
+    assert b64 == hi[capable].sum() + c_fp64[~capable].sum()
 
 
 def test_mixed_and_fp32_only_benzene(torch_cuda):
