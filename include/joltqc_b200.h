@@ -37,7 +37,7 @@ typedef struct jqc_engine jqc_engine;
  * produced by split_basis :678-837 and sort_group_basis :483-675).  All arrays are HOST
  * pointers and are copied. */
 typedef struct jqc_basis_desc {
-    int nbas;                 /* padded shell count, multiple of JQC_TILE, <= 65535 (jk.py:43-45) */
+    int nbas;                 /* padded shell count, multiple of JQC_TILE, <= 57344 (the reference allows 65535, jk.py:43-45) */
     const double* records;    /* nbas x 12: x,y,z,ao_loc,c0,e0,c1,e1,c2,e2,0,0 (basis.py:326-371) */
     const int* angs;          /* nbas */
     const int* nprims;        /* nbas */

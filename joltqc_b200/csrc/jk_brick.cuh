@@ -86,11 +86,14 @@ inline void brick_decompose(BrickArgs& b, int per_task, int nsm)
 }
 
 // One shell quartet, all in registers: eri[N] += contracted integrals (reference: 1q1t.cu:86-405).
-template <int LI, int LJ, int LK, int LL>
+// KET_REG: the first primitive-pair record of the lane's ket pair arrives in registers (kr0, kr1; it is the
+// same for every quartet of a brick), so single-primitive kets issue no table load per quartet.
+template <int LI, int LJ, int LK, int LL, bool KET_REG = false>
 __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const double* __restrict__ bra,
                                                const double* __restrict__ ket, const double4 ri, const double4 rj,
                                                const double4 rk, const double4 rl, const int npij, const int npkl,
-                                               const double omega, const double fac, const double2* __restrict__ s_rys)
+                                               const double omega, const double fac, const double2* __restrict__ s_rys,
+                                               const double4 kr0 = double4(), const double4 kr1 = double4())
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
@@ -101,8 +104,12 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
     for (int n = 0; n < N; n++) eri[n] = 0.0;
 #pragma unroll 1
     for (int klp = 0; klp < npkl; klp++) {
-        const double4 k0 = *reinterpret_cast<const double4*>(ket + klp * 8);
-        const double4 k1 = *reinterpret_cast<const double4*>(ket + klp * 8 + 4);
+        double4 k0, k1;
+        if (KET_REG && klp == 0) { k0 = kr0; k1 = kr1; }
+        else {
+            k0 = *reinterpret_cast<const double4*>(ket + klp * 8);
+            k1 = *reinterpret_cast<const double4*>(ket + klp * 8 + 4);
+        }
         const double akl = k0.x, inv_akl = k0.y, al_akl = k0.z, ckcl = k0.w;
         const double qx = k1.x, qy = k1.y, qz = k1.z;
 #pragma unroll 1
@@ -113,9 +120,10 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
             const double cicj = fac * b0.w;
             const double Rpq[3] = {b1.x - qx, b1.y - qy, b1.z - qz};
             const double rr = Rpq[0] * Rpq[0] + Rpq[1] * Rpq[1] + Rpq[2] * Rpq[2];
-            const double inv_aijkl = 1.0 / (aij + akl);
+            const double rs_aijkl = jrsqrt(aij + akl);
+            const double inv_aijkl = rs_aijkl * rs_aijkl;
             const double theta = aij * akl * inv_aijkl;
-            const double gy0 = cicj * inv_aij * inv_akl * sqrt(inv_aijkl);
+            const double gy0 = cicj * inv_aij * inv_akl * rs_aijkl;
             double rw[2 * NROOTS];
             double theta_fac = 1.0, sqrt_theta_fac = 1.0;
             if (omega > 0.0) {
@@ -223,11 +231,12 @@ __device__ __forceinline__ void fill_g_t(R* __restrict__ g, const R seed0, const
     }
 }
 
-template <int LI, int LJ, int LK, int LL>
+template <int LI, int LJ, int LK, int LL, bool KET_REG = false>
 __device__ __forceinline__ void eri_block_regs_f(float* __restrict__ eri, const double* __restrict__ bra,
                                                  const double* __restrict__ ket, const double4 ri, const double4 rj,
                                                  const double4 rk, const double4 rl, const int npij, const int npkl,
-                                                 const float omega, const float fac, const float2* __restrict__ s_rys)
+                                                 const float omega, const float fac, const float2* __restrict__ s_rys,
+                                                 const double4 kr0 = double4(), const double4 kr1 = double4())
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
     constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
@@ -238,8 +247,12 @@ __device__ __forceinline__ void eri_block_regs_f(float* __restrict__ eri, const 
     for (int n = 0; n < N; n++) eri[n] = 0.0f;
 #pragma unroll 1
     for (int klp = 0; klp < npkl; klp++) {
-        const double4 k0 = *reinterpret_cast<const double4*>(ket + klp * 8);
-        const double4 k1 = *reinterpret_cast<const double4*>(ket + klp * 8 + 4);
+        double4 k0, k1;
+        if (KET_REG && klp == 0) { k0 = kr0; k1 = kr1; }
+        else {
+            k0 = *reinterpret_cast<const double4*>(ket + klp * 8);
+            k1 = *reinterpret_cast<const double4*>(ket + klp * 8 + 4);
+        }
         const float akl = (float)k0.x, inv_akl = (float)k0.y, al_akl = (float)k0.z, ckcl = (float)k0.w;
 #pragma unroll 1
         for (int ipj = 0; ipj < npij; ipj++) {
@@ -249,9 +262,10 @@ __device__ __forceinline__ void eri_block_regs_f(float* __restrict__ eri, const 
             const float cicj = fac * (float)b0.w;
             const float Rpq[3] = {(float)(b1.x - k1.x), (float)(b1.y - k1.y), (float)(b1.z - k1.z)};
             const float rr = Rpq[0] * Rpq[0] + Rpq[1] * Rpq[1] + Rpq[2] * Rpq[2];
-            const float inv_aijkl = 1.0f / (aij + akl);
+            const float rs_aijkl = jrsqrt(aij + akl);
+            const float inv_aijkl = rs_aijkl * rs_aijkl;
             const float theta = aij * akl * inv_aijkl;
-            const float gy0 = cicj * inv_aij * inv_akl * sqrtf(inv_aijkl);
+            const float gy0 = cicj * inv_aij * inv_akl * rs_aijkl;
             float rw[2 * NROOTS];
             float theta_fac = 1.0f, sqrt_theta_fac = 1.0f;
             if (omega > 0.0f) {
@@ -295,6 +309,10 @@ __device__ __forceinline__ void eri_block_regs_f(float* __restrict__ eri, const 
         }
     }
 }
+
+#ifndef JQC_BRICK_PIPE_N
+#define JQC_BRICK_PIPE_N 1
+#endif
 
 // Per-class layout of the brick kernel, usable at compile time (BrickPlan) and by the host (which
 // classes are supported, how much dynamic shared memory a launch needs).  f32 = the FP32-band
@@ -361,6 +379,14 @@ struct BrickPlan {
     static constexpr size_t SMEM = B.smem, RYS_BYTES = B.rys_bytes;
     // density-block slot offsets (lane-private reals)
     static constexpr int S_DI = 0, S_DLK = DI_SMEM ? NKI : 0;
+    // The smallest blocks are latency-, not FP64-bound (profiles/r2: long-scoreboard stalls on the dependent
+    // list -> shell -> log-density loads of every j step and on the table / density loads of every
+    // quartet).  PIPE runs the j loop software-pipelined (list entries two steps ahead, the data that
+    // depend on the partner shell one step ahead), loads the density blocks of the digestion before the
+    // integrals and keeps the ket's first primitive-pair record in registers for the whole brick.
+    // Measured (profiles/r2/class_times_21_pipe54.csv): (ss|ss) -15 %, every larger class loses 0-35 %
+    // to the extra live registers, hence the threshold of one integral.
+    static constexpr bool PIPE = B.n <= JQC_BRICK_PIPE_N;
 };
 
 template <class R> struct BrickRysTab { using type = double2; };
@@ -434,6 +460,11 @@ jk_brick_kernel(const BrickArgs a)
         const int k0 = (int)rk.w, l0 = (int)rl.w;
         const float d_kl = a.logd[(size_t)ksh * nbas + lsh];
         const double* __restrict__ ket = a.ket_tab + (size_t)pp * npkl * 8;
+        double4 kr0 = double4(), kr1 = double4();
+        if constexpr (P::PIPE) {
+            kr0 = *reinterpret_cast<const double4*>(ket);
+            kr1 = *reinterpret_cast<const double4*>(ket + 4);
+        }
 
         double jkl[DO_J ? NFK * NFL : 1];
         R dlk_r[(DO_J && P::DLK_MODE == 0) ? NFK * NFL : 1];
@@ -490,12 +521,46 @@ jk_brick_kernel(const BrickArgs a)
             }
             bool touched_i = false;
 
+            // pipeline registers: list entry e + 1 (n1), entry e + 2 (n2), partner-shell data of e + 1 (m1)
+            struct L1 { float q, tq; int jsh; };
+            struct L2 { float d_jk, d_jl, d_ij; double4 rj; };
+            auto load1 = [&](int x) -> L1 {
+                const int xc = min(x, e_end - 1);
+                return L1{a.j_q[xc], a.j_tq[xc], (int)a.j_idx[xc]};
+            };
+            auto load2 = [&](const L1& l) -> L2 {
+                L2 r;
+                r.d_jk = DO_K ? a.logd[(size_t)l.jsh * nbas + ksh] : 0.f;
+                r.d_jl = DO_K ? a.logd[(size_t)l.jsh * nbas + lsh] : 0.f;
+                r.d_ij = DO_J ? a.logd[(size_t)ish * nbas + l.jsh] : 0.f;
+                r.rj = *reinterpret_cast<const double4*>(a.basis + l.jsh * BASIS_STRIDE);
+                return r;
+            };
+            L1 n1 = L1(), n2 = L1();
+            L2 m1 = L2();
+            if constexpr (P::PIPE) {
+                n1 = load1(e);
+                n2 = load1(e + 1);
+                m1 = load2(n1);
+            }
 #pragma unroll 1
             for (; e < e_end; e++) {
-                const float q_ij = a.j_q[e];
+                float q_ij, tq_ij, pd_jk = 0.f, pd_jl = 0.f, pd_ij = 0.f;
+                int jsh;
+                double4 rj;
+                if constexpr (P::PIPE) {
+                    q_ij = n1.q; tq_ij = n1.tq; jsh = n1.jsh;
+                    pd_jk = m1.d_jk; pd_jl = m1.d_jl; pd_ij = m1.d_ij; rj = m1.rj;
+                    n1 = n2;
+                    m1 = load2(n1);          // entry e + 1: its shell index arrived one step ago
+                    n2 = load1(e + 2);
+                } else {
+                    q_ij = a.j_q[e];
+                }
                 if (!(q_ij + Qb + dmaxf > a.cutoff)) break;         // q-descending list: nothing further passes
-                if (!((double)a.j_tq[e] > paircut)) continue;      // bra tile pair not active
-                const int jsh = a.j_idx[e];
+                if constexpr (!P::PIPE) tq_ij = a.j_tq[e];
+                if (!((double)tq_ij > paircut)) continue;           // bra tile pair not active
+                if constexpr (!P::PIPE) jsh = a.j_idx[e];
                 // canonical order (screen_jk_tasks.cu:202, 225, 239) + Schwarz x density test (:241-261)
                 bool live = lane_i && (!a.tri || ksh < ish || lsh <= jsh);
                 if (live) {
@@ -503,12 +568,12 @@ jk_brick_kernel(const BrickArgs a)
                     float d_large = -36.8f;
                     if constexpr (DO_K) {
                         d_large = fmaxf(d_large, d_ik);
-                        d_large = fmaxf(d_large, a.logd[(size_t)jsh * nbas + ksh]);
+                        d_large = fmaxf(d_large, P::PIPE ? pd_jk : a.logd[(size_t)jsh * nbas + ksh]);
                         d_large = fmaxf(d_large, d_il);
-                        d_large = fmaxf(d_large, a.logd[(size_t)jsh * nbas + lsh]);
+                        d_large = fmaxf(d_large, P::PIPE ? pd_jl : a.logd[(size_t)jsh * nbas + lsh]);
                     }
                     if constexpr (DO_J) {
-                        d_large = fmaxf(d_large, a.logd[(size_t)ish * nbas + jsh]);
+                        d_large = fmaxf(d_large, P::PIPE ? pd_ij : a.logd[(size_t)ish * nbas + jsh]);
                         d_large = fmaxf(d_large, d_kl);
                     }
                     // precision band of this launch (screen_jk_tasks.cu:258-261: sel_fp64 = dq > cutoff_fp64)
@@ -520,28 +585,50 @@ jk_brick_kernel(const BrickArgs a)
                 if (lane == 0) nq += __popc(m);
                 touched_i |= live;
 
-                const double* __restrict__ bj = a.basis + jsh * BASIS_STRIDE;
-                const double4 rj = *reinterpret_cast<const double4*>(bj);
+                if constexpr (!P::PIPE) rj = *reinterpret_cast<const double4*>(a.basis + jsh * BASIS_STRIDE);
                 const int j0 = (int)rj.w;
+                // density blocks of the digestion, requested before the integrals so that their latency
+                // hides behind the ERI evaluation (small blocks only: they stay live in registers)
+                R d_ji[(DO_J && P::PIPE) ? NFI * NFJ : 1], d_jl[(DO_K && P::PIPE) ? NFJ * NFL : 1], d_jk[(DO_K && P::PIPE) ? NFJ * NFK : 1];
+                if constexpr (P::PIPE) {
+                    if constexpr (DO_J) {
+#pragma unroll
+                        for (int i = 0; i < NFI; i++)
+#pragma unroll
+                        for (int j = 0; j < NFJ; j++) d_ji[i * NFJ + j] = ldd((size_t)(j0 + j) * nao + i0 + i);
+                    }
+                    if constexpr (DO_K) {
+#pragma unroll
+                        for (int j = 0; j < NFJ; j++) {
+#pragma unroll
+                            for (int l = 0; l < NFL; l++) d_jl[j * NFL + l] = ldd((size_t)(j0 + j) * nao + l0 + l);
+#pragma unroll
+                            for (int k = 0; k < NFK; k++) d_jk[j * NFK + k] = ldd((size_t)(j0 + j) * nao + k0 + k);
+                        }
+                    }
+                }
                 R fac = live ? R(PI_FAC) : R(0);
                 if (ish == jsh) fac *= R(0.5);
                 if (ksh == lsh) fac *= R(0.5);
                 if (ish == ksh && jsh == lsh) fac *= R(0.5);
                 R eri[N];
                 if constexpr (F32)
-                    eri_block_regs_f<LI, LJ, LK, LL>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
-                                                     npkl, (float)a.omega, fac, s_rys);
+                    eri_block_regs_f<LI, LJ, LK, LL, P::PIPE>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
+                                                              npkl, (float)a.omega, fac, s_rys, kr0, kr1);
                 else
-                    eri_block_regs<LI, LJ, LK, LL>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
-                                                   npkl, a.omega, fac, s_rys);
+                    eri_block_regs<LI, LJ, LK, LL, P::PIPE>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
+                                                            npkl, a.omega, fac, s_rys, kr0, kr1);
 #define ERI_(i, j, k, l) eri[(((i) * NFJ + (j)) * NFK + (k)) * NFL + (l)]
                 if constexpr (DO_J) {
                     // J_kl += sum_ij (ij|kl) D[j,i]: lane-stationary
-                    R d_ji[NFI * NFJ];
+                    R d_ji_l[P::PIPE ? 1 : NFI * NFJ];
+                    if constexpr (!P::PIPE) {
 #pragma unroll
-                    for (int i = 0; i < NFI; i++)
+                        for (int i = 0; i < NFI; i++)
 #pragma unroll
-                    for (int j = 0; j < NFJ; j++) d_ji[i * NFJ + j] = ldd((size_t)(j0 + j) * nao + i0 + i);
+                        for (int j = 0; j < NFJ; j++) d_ji_l[i * NFJ + j] = ldd((size_t)(j0 + j) * nao + i0 + i);
+                    }
+                    const R* __restrict__ d_ji_p = P::PIPE ? d_ji : d_ji_l;
 #pragma unroll
                     for (int k = 0; k < NFK; k++)
 #pragma unroll
@@ -551,14 +638,14 @@ jk_brick_kernel(const BrickArgs a)
 #pragma unroll
                             for (int i = 0; i < NFI; i++)
 #pragma unroll
-                            for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji[i * NFJ + j], s);
+                            for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji_p[i * NFJ + j], s);
                             jkl[k * NFL + l] += (double)s;
                         } else {
                             R s = (R)jkl[k * NFL + l];
 #pragma unroll
                             for (int i = 0; i < NFI; i++)
 #pragma unroll
-                            for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji[i * NFJ + j], s);
+                            for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji_p[i * NFJ + j], s);
                             jkl[k * NFL + l] = s;
                         }
                     }
@@ -589,11 +676,14 @@ jk_brick_kernel(const BrickArgs a)
                 }
                 if constexpr (DO_K) {
                     {   // K_ik += sum_jl (ij|kl) D[j,l]: stationary over the j loop
-                        R d[NFJ * NFL];
+                        R d_l[P::PIPE ? 1 : NFJ * NFL];
+                        if constexpr (!P::PIPE) {
 #pragma unroll
-                        for (int j = 0; j < NFJ; j++)
+                            for (int j = 0; j < NFJ; j++)
 #pragma unroll
-                        for (int l = 0; l < NFL; l++) d[j * NFL + l] = ldd((size_t)(j0 + j) * nao + l0 + l);
+                            for (int l = 0; l < NFL; l++) d_l[j * NFL + l] = ldd((size_t)(j0 + j) * nao + l0 + l);
+                        }
+                        const R* __restrict__ d = P::PIPE ? d_jl : d_l;
 #pragma unroll
                         for (int i = 0; i < NFI; i++)
 #pragma unroll
@@ -608,11 +698,14 @@ jk_brick_kernel(const BrickArgs a)
                         }
                     }
                     {   // K_il += sum_jk (ij|kl) D[j,k]: stationary over the j loop
-                        R d[NFJ * NFK];
+                        R d_l[P::PIPE ? 1 : NFJ * NFK];
+                        if constexpr (!P::PIPE) {
 #pragma unroll
-                        for (int j = 0; j < NFJ; j++)
+                            for (int j = 0; j < NFJ; j++)
 #pragma unroll
-                        for (int k = 0; k < NFK; k++) d[j * NFK + k] = ldd((size_t)(j0 + j) * nao + k0 + k);
+                            for (int k = 0; k < NFK; k++) d_l[j * NFK + k] = ldd((size_t)(j0 + j) * nao + k0 + k);
+                        }
+                        const R* __restrict__ d = P::PIPE ? d_jk : d_l;
 #pragma unroll
                         for (int i = 0; i < NFI; i++)
 #pragma unroll

@@ -288,9 +288,10 @@ jk_bwarp_kernel(const BrickArgs a)
                             const R cicj = fac * (R)b0.w;
                             const R Rpq[3] = {(R)(b1.x - qx), (R)(b1.y - qy), (R)(b1.z - qz)};
                             const R rr = Rpq[0] * Rpq[0] + Rpq[1] * Rpq[1] + Rpq[2] * Rpq[2];
-                            const R inv_aijkl = R(1) / (aij + akl);
+                            const R rs_aijkl = jrsqrt(aij + akl);
+                            const R inv_aijkl = rs_aijkl * rs_aijkl;
                             const R theta = aij * akl * inv_aijkl;
-                            const R gy0 = cicj * inv_aij * inv_akl * sqrt(inv_aijkl);
+                            const R gy0 = cicj * inv_aij * inv_akl * rs_aijkl;
                             R theta_fac = R(1), sqrt_theta_fac = R(1);
                             if (a.omega > 0.0) {
                                 const R o2 = (R)(a.omega * a.omega);

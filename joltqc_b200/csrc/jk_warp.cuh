@@ -38,9 +38,9 @@ __device__ __forceinline__ void rys_root_one(double x, int i, double& root, doub
     constexpr int TRI = NROOTS * (NROOTS - 1) / 2;
     constexpr double large_x = NROOTS * 5 + 35;
     if (x >= large_x) {
-        const double inv_x = 1.0 / x;
-        root = RYS_LARGEX[(TRI + i) * 2] * inv_x;
-        weight = RYS_LARGEX[(TRI + i) * 2 + 1] * (SQRTPIE4 * sqrt(inv_x));
+        const double rs_x = jrsqrt(x);
+        root = RYS_LARGEX[(TRI + i) * 2] * (rs_x * rs_x);
+        weight = RYS_LARGEX[(TRI + i) * 2 + 1] * (SQRTPIE4 * rs_x);
         return;
     }
     const RysPowers p = rys_powers(x);
@@ -58,9 +58,9 @@ __device__ __forceinline__ void rys_root_one_smem(double x, int i, double& root,
     constexpr int TRI = NROOTS * (NROOTS - 1) / 2;
     constexpr double large_x = NROOTS * 5 + 35;
     if (x >= large_x) {
-        const double inv_x = 1.0 / x;
-        root = RYS_LARGEX[(TRI + i) * 2] * inv_x;
-        weight = RYS_LARGEX[(TRI + i) * 2 + 1] * (SQRTPIE4 * sqrt(inv_x));
+        const double rs_x = jrsqrt(x);
+        root = RYS_LARGEX[(TRI + i) * 2] * (rs_x * rs_x);
+        weight = RYS_LARGEX[(TRI + i) * 2 + 1] * (SQRTPIE4 * rs_x);
         return;
     }
     const RysPowers p = rys_powers(x);
@@ -257,7 +257,17 @@ struct WarpPlan {
     static constexpr int QPW = 32 / T;
     static constexpr int NKLP = (NKL + T - 1) / T;
     static constexpr int DKP = WarpLayout<LI, LJ, LK, LL>::DKP, DLP = DKP * (LK + 1), GSP = DLP * (LL + 1);
-    static constexpr int IS = GSP | 1;                  // stride between (root, direction) arrays: odd
+    // stride between the (root, direction) arrays: the generated layout's value modulo 16 (recurrence
+    // phase: the lanes of a round access the same offset of different arrays), else odd
+    static constexpr int array_stride()
+    {
+        constexpr int want = WarpLayout<LI, LJ, LK, LL>::IS16;
+        if (want < 0) return GSP | 1;
+        int v = GSP;
+        while (v % 16 != want) v++;
+        return v;
+    }
+    static constexpr int IS = array_stride();
     static constexpr int G_ALL = S::NROOTS * 3 * IS;
     static constexpr int NDBLK = NIJ + NKL + S::NFJ * S::NFL + S::NFJ * S::NFK + S::NFI * S::NFL + S::NFI * S::NFK;
     static constexpr int STAGE = 2 * NKL * (S::NFI + S::NFJ) + T * NIJ;
@@ -435,9 +445,10 @@ jk_warp_kernel(const JKArgs a)
                     const double Rpq[3] = {fma(rjri[0], aj_aij, ri.x) - qx, fma(rjri[1], aj_aij, ri.y) - qy,
                                            fma(rjri[2], aj_aij, ri.z) - qz};
                     const double rr = Rpq[0] * Rpq[0] + Rpq[1] * Rpq[1] + Rpq[2] * Rpq[2];
-                    const double inv_aijkl = 1.0 / (aij + akl);
+                    const double rs_aijkl = jrsqrt(aij + akl);
+                    const double inv_aijkl = rs_aijkl * rs_aijkl;
                     const double theta = aij * akl * inv_aijkl;
-                    const double gy0 = cicj * inv_aij * inv_akl * sqrt(inv_aijkl);
+                    const double gy0 = cicj * inv_aij * inv_akl * rs_aijkl;
                     double theta_fac = 1.0, sqrt_theta_fac = 1.0;
                     if (a.omega > 0.0) {
                         const double o2 = a.omega * a.omega;

@@ -83,6 +83,11 @@ struct ShellHead {
 // u, u^2, u^4, u^8 shared by all 2 n series of a quartet, so the evaluation is throughput- and not
 // latency-bound at the 2-4 resident warps per scheduler these kernels run with.
 // rw[2i] = root, rw[2i+1] = weight.
+// 1/sqrt in one MUFU + Newton step; the kernels derive both 1/p and 1/sqrt(p) from it (a division plus
+// a square root cost about three times as many instructions)
+__device__ __forceinline__ double jrsqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ float jrsqrt(float x) { return rsqrtf(x); }
+
 struct RysPowers {
     double u, u2, u4, u8;
     int it;
@@ -131,8 +136,9 @@ __device__ __forceinline__ void rys_roots(double x, double* __restrict__ rw)
     constexpr int TRI = NROOTS * (NROOTS - 1) / 2;
     constexpr double large_x = NROOTS * 5 + 35;
     if (x >= large_x) {
-        const double inv_x = 1.0 / x;
-        const double t = SQRTPIE4 * sqrt(inv_x);
+        const double rs_x = jrsqrt(x);
+        const double inv_x = rs_x * rs_x;
+        const double t = SQRTPIE4 * rs_x;
 #pragma unroll
         for (int i = 0; i < NROOTS; i++) {
             rw[2 * i] = RYS_LARGEX[(TRI + i) * 2] * inv_x;
@@ -181,8 +187,9 @@ __device__ __forceinline__ void rys_roots_smem(double x, double* __restrict__ rw
     constexpr int TRI = NROOTS * (NROOTS - 1) / 2;
     constexpr double large_x = NROOTS * 5 + 35;
     if (x >= large_x) {
-        const double inv_x = 1.0 / x;
-        const double t = SQRTPIE4 * sqrt(inv_x);
+        const double rs_x = jrsqrt(x);
+        const double inv_x = rs_x * rs_x;
+        const double t = SQRTPIE4 * rs_x;
 #pragma unroll
         for (int i = 0; i < NROOTS; i++) {
             rw[2 * i] = RYS_LARGEX[(TRI + i) * 2] * inv_x;
@@ -229,8 +236,9 @@ __device__ __forceinline__ void rys_roots_smem_f(float x, float* __restrict__ rw
     constexpr int TRI = NROOTS * (NROOTS - 1) / 2;
     constexpr float large_x = NROOTS * 5 + 35;
     if (x >= large_x) {
-        const float inv_x = 1.0f / x;
-        const float t = (float)SQRTPIE4 * sqrtf(inv_x);
+        const float rs_x = jrsqrt(x);
+        const float inv_x = rs_x * rs_x;
+        const float t = (float)SQRTPIE4 * rs_x;
 #pragma unroll
         for (int i = 0; i < NROOTS; i++) {
             rw[2 * i] = (float)RYS_LARGEX[(TRI + i) * 2] * inv_x;
