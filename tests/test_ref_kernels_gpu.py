@@ -11,12 +11,16 @@ from tests.common import H2O, benzene, make, random_dm
 pytestmark = pytest.mark.gpu
 
 
-def _compare(atom, basis, seed, scale=1.0, tol=1e-10):
+def _compare(atom, basis, seed, scale=1.0, tol=1e-10, mol=None):
     import torch
     from oracle.ref_kernels import runner
     if not runner.available():
         pytest.skip("oracle/_ref not built (needs the reference tree at build time)")
-    mol, lay = make(atom, basis)
+    if mol is None:
+        mol, lay = make(atom, basis)
+    else:
+        from joltqc_b200.pyscf.basis import BasisLayout
+        lay = BasisLayout.from_mol(mol, alignment=4)
     eng = lay.engine()
     ref = runner.RefJK(lay, eng)
     missing = ref.missing_kernels()
@@ -42,3 +46,11 @@ def test_h2o_tzvpp_vs_reference_kernels():
 
 def test_benzene_ccpvtz_vs_reference_kernels():
     _compare(benzene(), "cc-pvtz", 9, scale=1.0 / 264)
+
+
+def test_taxol_svp_vs_reference_kernels():
+    """BASELINE config 3 (taxol stand-in / def2-SVP, 1e9 quartets): a molecule large enough that every
+    brick / multi-lane launch runs many tasks per warp, element-wise against the reference's kernels"""
+    import bench
+    mol, _ = bench.build_mol("taxol-svp")
+    _compare(None, None, 11, scale=1.0 / mol.nao, mol=mol)

@@ -1,6 +1,8 @@
 # scratch driver for one gpurun call (A/B timings + ncu captures); edited per experiment
 set -x
-python -m pytest tests/test_jk_gpu.py -x -q > gpurun_out/tests_r2_22.txt 2>&1; tail -3 gpurun_out/tests_r2_22.txt
-python tools/class_profile.py gpurun_out/class_times_r2_22.csv 2>&1 | tail -1
-JQC_BWARP=2 python tools/class_profile.py gpurun_out/class_times_r2_22_bw2.csv 2>&1 | tail -1
-JQC_BWARP=0 python tools/class_profile.py gpurun_out/class_times_r2_22_bw0.csv 2>&1 | tail -1
+python tools/class_profile.py gpurun_out/class_times_r2_23.csv 2>&1 | tail -1
+python tools/class_profile.py gpurun_out/class_times_r2_23_mixed.csv valinomycin-tzvp ones 1e-7 2>&1 | tail -1
+M=gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active
+timeout 700 ncu --replay-mode application --clock-control none --metrics $M -k regex:jk_ --csv --log-file gpurun_out/ncu_fp64_per_launch_r2_23.csv python tools/one_build.py valinomycin-tzvp 1 2>&1 | tail -2
+python tools/ncu_fp64_classes.py gpurun_out/ncu_fp64_per_launch_r2_23.csv 34.2 > gpurun_out/ncu_fp64_per_kernel_r2_23.csv; wc -l gpurun_out/ncu_fp64_per_kernel_r2_23.csv; head -5 gpurun_out/ncu_fp64_per_kernel_r2_23.csv
+ls -la gpurun_out/*r2_23*
