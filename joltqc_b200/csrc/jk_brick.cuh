@@ -310,6 +310,14 @@ __device__ __forceinline__ void eri_block_regs_f(float* __restrict__ eri, const 
     }
 }
 
+// register budgets of the FP64 brick kernel by live doubles (integrals + stationary sums): 128 registers up to
+// LIVE128, 168 up to LIVE168, 255 above
+#ifndef JQC_BRICK_LIVE128
+#define JQC_BRICK_LIVE128 12
+#endif
+#ifndef JQC_BRICK_LIVE168
+#define JQC_BRICK_LIVE168 36
+#endif
 #ifndef JQC_BRICK_PIPE_N
 #define JQC_BRICK_PIPE_N 1
 #endif
@@ -344,7 +352,7 @@ __host__ __device__ constexpr BrickShape brick_shape(int li, int lj, int lk, int
         b.acc_smem = live > 80 && b.nki > 12;
         b.di_smem = b.nki <= 48;
         // register budget per thread -> CTAs of 128 threads per SM: 255 -> 2, 168 -> 3, 128 -> 4
-        b.regs = live <= 12 ? 128 : (live <= 36 ? 168 : 255);
+        b.regs = live <= JQC_BRICK_LIVE128 ? 128 : (live <= JQC_BRICK_LIVE168 ? 168 : 255);
         b.rys_bytes = (size_t)b.nroots * (14 + 2 * b.nroots) * (RYS_NCOEF + 1) * 16;
     } else {
         // 32-bit registers: integrals + g arrays (float) + double accumulators
