@@ -295,7 +295,7 @@ def mixed_leg(eng, dm_dev, vj64, vk64, cutoff_fp64=1e-7):
     (n64, n32), _ = eng.last_band_stats()
     return {"s_per_build": e0.elapsed_time(e1) * 1e-3, "cutoff_fp64": cutoff_fp64, "cutoff_fp32": 1e-13,
             "quartets_fp64": n64, "quartets_fp32": n32,
-            "fp32_kernels": "angular classes with <= 108 integrals (brick kernel, float integrals, FP64 accumulation); larger classes evaluate their band in FP64",
+            "fp32_kernels": "every angular class up to f shells (float integrals, FP64 accumulation: brick kernel <= 108 integrals, brick-scheduled multi-lane kernel above); classes with g shells and > 108 integrals evaluate their band in FP64",
             "max_abs_dJ_vs_fp64": float((vj - vj64).abs().max().item()), "max_abs_dK_vs_fp64": float((vk - vk64).abs().max().item()),
             "max_abs_J": float(vj64.abs().max().item()), "max_abs_K": float(vk64.abs().max().item()),
             "stated_tolerance": "max-abs 1e-7 x max(1, max|J|) on J and K (reference tests: 1e-7, jqc/pyscf/tests/test_jk.py:245-246)"}
