@@ -21,7 +21,7 @@ def brick_fits(li, lj, lk, ll):
     acc, di = live > 80 and nki > 12, nki <= 48
     dlk = 0 if njkl <= 3 else (1 if njkl <= 9 else 2)
     slots = (nki if acc else 0) + (nki if di else 0) + (njkl if dlk == 1 else 0)
-    regs = 128 if live <= 12 else (168 if live <= 36 else 255)
+    regs = 128 if live <= 12 else (168 if live <= 36 else 255)   # JQC_BRICK_LIVE128 / JQC_BRICK_LIVE168
     minb = 65536 // (regs * 128)
     smem = nroots * (14 + 2 * nroots) * 15 * 16 + 4 * 32 * slots * 8
     return n <= 108 and smem * minb <= 216 * 1024
@@ -29,7 +29,7 @@ def brick_fits(li, lj, lk, ll):
 names = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 funcs = re.findall(r"Function : (\S+)", names)
 os.makedirs(OUT, exist_ok=True)
-index = ["class,kernel,registers,stack_bytes,sass_lines,DFMA,DMUL,DADD,LDS,STS,LDG,REDG,SHFL,file"]
+index = ["class,kernel,registers,stack_bytes,sass_lines,DFMA,DMUL,DADD,LDS,STS,LDG,REDG,SHFL,file,fp32_twin_registers,fp32_twin_stack_bytes"]
 res = subprocess.run(["cuobjdump", "--dump-resource-usage", LIB], capture_output=True, text=True).stdout
 usage = {m[0]: (m[1], m[2]) for m in re.findall(r"Function (\S+):\n\s+REG:(\d+) STACK:(\d+)", res)}
 blocks = names.split("\t\tFunction : ")
@@ -40,9 +40,9 @@ for li in range(lmax + 1):
             for ll in range(lk + 1):
                 key = "%d%d%d%d" % (li, lj, lk, ll)
                 if brick_fits(li, lj, lk, ll):
-                    pat = "jk_brick_kernelILi%dELi%dELi%dELi%dELb1ELb1EEE" % (li, lj, lk, ll)
+                    pat = "jk_brick_kernelIdLi%dELi%dELi%dELi%dELb1ELb1EEE" % (li, lj, lk, ll)
                 elif key in bw:
-                    pat = "jk_bwarp_kernelILi%dELi%dELi%dELi%dELb1ELb1E" % (li, lj, lk, ll)
+                    pat = "jk_bwarp_kernelIdLi%dELi%dELi%dELi%dELb1ELb1E" % (li, lj, lk, ll)
                 else:
                     pat = "jk_warp_kernelILi%dELi%dELi%dELi%dELb1ELb1E" % (li, lj, lk, ll)
                 f = [x for x in funcs if pat in x]
@@ -58,6 +58,7 @@ for li in range(lmax + 1):
                     g.write("\t\tFunction : " + txt)
                 reg, stack = usage.get(fn, ("?", "?"))
                 index.append(",".join(["(%d%d|%d%d)" % (li, lj, lk, ll), re.search(r"jk_[a-z0-9_]+kernel(_small)?", fn).group(0), reg, stack,
-                                       str(txt.count("\n"))] + [str(ops[o]) for o in ("DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "REDG", "SHFL")] + [fname]))
+                                       str(txt.count("\n"))] + [str(ops[o]) for o in ("DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "REDG", "SHFL")] + [fname] +
+                                      list(usage.get(fn.replace("kernelId", "kernelIf"), ("", "")) if "kernelId" in fn else ("", "")) ))
 open(os.path.join(OUT, "INDEX.csv"), "w").write("\n".join(index) + "\n")
 print(len(index) - 1, "listings written to", OUT)
