@@ -60,8 +60,10 @@ void jqc_engine_destroy(jqc_engine* eng);
 const char* jqc_last_error(void);
 
 /* Static work partition for multi-GPU builds (the reference is single-GPU,
- * README.md:104): this engine evaluates only the (ij)-tile slices assigned to `rank` of
- * `world`.  The caller sums the partial buffers of all ranks (one NCCL allreduce). */
+ * README.md:104): this engine evaluates only the tasks assigned to `rank` of `world` -- a
+ * deterministic interleave of the Schwarz-sorted task lists whose direction alternates from
+ * round to round, so that every rank receives the same mix of heavy and light tasks.  The
+ * caller sums the partial buffers of all ranks (one NCCL allreduce). */
 int jqc_engine_set_shard(jqc_engine* eng, int rank, int world);
 
 /* log-Schwarz matrix q[i,j] = log(sqrt(max|(ab|ab)|)+1e-300), float32 (nbas x nbas), pads

@@ -655,8 +655,9 @@ extern "C" int jqc_build_partial(jqc_engine* e, const double* dm_dev, int n_dm, 
             if (rc) return rc;
             continue;
         }
-        // quartet-list path: this rank owns list entries rank, rank + world, ... of the ij tile list
-        const int n_ij = (n_ij_all - e->rank + e->world - 1) / e->world;
+        // quartet-list path: this rank owns entries shard_entry(0, rank, world), shard_entry(1, ...), ... of the
+        // q-sorted ij tile list (slots past the end of the list are masked in the kernel)
+        const int n_ij = (n_ij_all + e->world - 1) / e->world;
         if (n_ij <= 0) continue;
         // chunk so that 256 * ij_tiles * kl_tiles <= queue capacity (and the grid's y extent <= 65535)
         const int kl_chunk = std::min({n_kl, e->kl_chunk_max, (int)(e->queue_cap / 256)});

@@ -98,7 +98,7 @@ struct ScreenArgs {
     const float* __restrict__ tileq_kl;  // tile max q aligned with tiles_kl
     const int* __restrict__ nact_ij;     // device counts of active tiles in each list
     const int* __restrict__ nact_kl;
-    int ij_begin, ij_count;              // chunk of this rank's slots: list index = (ij_begin + s) * world + rank
+    int ij_begin, ij_count;              // chunk of this rank's slots: list index = shard_entry(ij_begin + s, rank, world)
     int kl_begin, kl_count;
     int rank, world;
     float cutoff;                        // log(cutoff_fp32): evaluate above this
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) screen_tasks_kernel(const ScreenArgs s)
     const int lane = threadIdx.x;
     const int kl_slot = blockIdx.x * 32 + lane;
     const int ij_slot = blockIdx.y * 8 + threadIdx.y;
-    const int ij_idx = (s.ij_begin + (ij_slot >> 4)) * s.world + s.rank;
+    const int ij_idx = (int)shard_entry((unsigned)(s.ij_begin + (ij_slot >> 4)), s.rank, s.world);
     const int pair = ij_slot & 15;
     bool active = (ij_slot >> 4) < s.ij_count && ij_idx < *s.nact_ij && kl_slot < s.kl_count &&
                   (s.kl_begin + kl_slot) < *s.nact_kl;

@@ -57,7 +57,7 @@ struct BrickArgs {
     const double* __restrict__ bra_tab;       // entry of j-list element e at (e - j_base) * npi * npj * 8
     const double* __restrict__ ket_tab;       // entry of ket pair p at p * npk * npl * 8
     int j_base;
-    int rank, world;                          // this GPU takes tasks rank, rank + world, ...
+    int rank, world;                          // this GPU takes tasks shard_entry(0, rank, world), shard_entry(1, ...), ...
     unsigned* __restrict__ work;              // dynamic task counter (zeroed per build)
     unsigned long long* __restrict__ qcount;  // evaluated quartets (accounting)
 };
@@ -442,7 +442,7 @@ jk_brick_kernel(const BrickArgs a)
     for (;;) {
         unsigned t = 0;
         if (lane == 0) t = atomicAdd(a.work, 1u);
-        t = __shfl_sync(FULL, t, 0) * (unsigned)a.world + (unsigned)a.rank;
+        t = shard_entry(__shfl_sync(FULL, t, 0), a.rank, a.world);
         if (t >= ntask) break;
         const int js = (int)(t % (unsigned)a.jsplit);
         t /= (unsigned)a.jsplit;

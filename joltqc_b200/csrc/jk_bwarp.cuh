@@ -142,7 +142,7 @@ jk_bwarp_kernel(const BrickArgs a)
     for (;;) {
         unsigned tk = 0;
         if (lane == 0) tk = atomicAdd(a.work, 1u);
-        tk = __shfl_sync(FULL, tk, 0) * (unsigned)a.world + (unsigned)a.rank;
+        tk = shard_entry(__shfl_sync(FULL, tk, 0), a.rank, a.world);
         if (tk >= ntask) break;
         const int js = (int)(tk % (unsigned)a.jsplit);
         tk /= (unsigned)a.jsplit;

@@ -67,6 +67,14 @@ __device__ __forceinline__ int float_to_ordered(float f)
 }
 __device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 
+// Static multi-GPU partition of a cost-sorted task list: round r of `world` consecutive entries goes to ranks
+// 0..world-1 when r is even and world-1..0 when r is odd (boustrophedon), so that a list sorted by descending
+// Schwarz bound (= descending cost) does not hand rank 0 the heaviest entry of every round.
+__host__ __device__ __forceinline__ unsigned shard_entry(unsigned round, int rank, int world)
+{
+    return round * (unsigned)world + (unsigned)((round & 1u) ? world - 1 - rank : rank);
+}
+
 // Packed record: [x, y, z, ao_loc, c0, e0, c1, e1, c2, e2, 0, 0]
 struct ShellHead {
     double x, y, z, ao;
