@@ -20,6 +20,8 @@
 //   * the Schwarz x density test of the reference (same float32 arithmetic, same canonical order,
 //     same tile-pair prefilter) runs per lane inside the loop: no quartet list, no second kernel.
 #pragma once
+#include <type_traits>
+
 #include "jk_1q1t.cuh"
 
 namespace jqc {
@@ -88,7 +90,9 @@ inline void brick_decompose(BrickArgs& b, int per_task, int nsm)
 // One shell quartet, all in registers: eri[N] += contracted integrals (reference: 1q1t.cu:86-405).
 // KET_REG: the first primitive-pair record of the lane's ket pair arrives in registers (kr0, kr1; it is the
 // same for every quartet of a brick), so single-primitive kets issue no table load per quartet.
-template <int LI, int LJ, int LK, int LL, bool KET_REG = false>
+// [I0, I1): the range of i components this call evaluates (eri holds (I1 - I0) * NFJ * NFK * NFL values); the
+// two-pass variant of the largest blocks calls it once per half so that only half the block is live.
+template <int LI, int LJ, int LK, int LL, bool KET_REG = false, int I0 = 0, int I1 = nf_of(LI)>
 __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const double* __restrict__ bra,
                                                const double* __restrict__ ket, const double4 ri, const double4 rj,
                                                const double4 rk, const double4 rl, const int npij, const int npkl,
@@ -96,8 +100,9 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
                                                const double4 kr0 = double4(), const double4 kr1 = double4())
 {
     using S = QuartetShape<LI, LJ, LK, LL>;
-    constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
+    constexpr int NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = (I1 - I0) * NFJ * NFK * NFL;
     constexpr int NROOTS = S::NROOTS, GS = S::GSIZE, DJ = S::DJ, DK = S::DK, DL = S::DL;
+    static_assert(0 <= I0 && I0 < I1 && I1 <= S::NFI, "i range");
     const double rjri[3] = {rj.x - ri.x, rj.y - ri.y, rj.z - ri.z};
     const double rlrk[3] = {rl.x - rk.x, rl.y - rk.y, rl.z - rk.z};
 #pragma unroll
@@ -150,7 +155,7 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
                 double g[3 * GS];
                 fill_g_small<LI, LJ, LK, LL>(g, ckcl, gy0, wt, c0, cp, b10, b01, b00, rjri, rlrk);
 #pragma unroll
-                for (int i = 0; i < NFI; i++)
+                for (int i = I0; i < I1; i++)
 #pragma unroll
                 for (int j = 0; j < NFJ; j++)
 #pragma unroll
@@ -160,7 +165,7 @@ __device__ __forceinline__ void eri_block_regs(double* __restrict__ eri, const d
                     const int ax = CART_X[LI][i] + CART_X[LJ][j] * DJ + CART_X[LK][k] * DK + CART_X[LL][l] * DL;
                     const int ay = CART_Y[LI][i] + CART_Y[LJ][j] * DJ + CART_Y[LK][k] * DK + CART_Y[LL][l] * DL;
                     const int az = CART_Z[LI][i] + CART_Z[LJ][j] * DJ + CART_Z[LK][k] * DK + CART_Z[LL][l] * DL;
-                    const int n = ((i * NFJ + j) * NFK + k) * NFL + l;
+                    const int n = (((i - I0) * NFJ + j) * NFK + k) * NFL + l;
                     eri[n] = fma(g[ax] * g[GS + ay], g[2 * GS + az], eri[n]);
                 }
             }
@@ -321,6 +326,14 @@ __device__ __forceinline__ void eri_block_regs_f(float* __restrict__ eri, const 
 #ifndef JQC_BRICK_PIPE_N
 #define JQC_BRICK_PIPE_N 1
 #endif
+// FP64 blocks of at least this many integrals (with an even number of i components and a ket other than (ss|)
+// are evaluated and digested in two passes over the halves of the i components: half the integral block is live
+// at a time (600-1000 B of spills per thread drop to 200-270 B) at the price of evaluating prefactors, roots and
+// recurrences twice.  Measured on valinomycin/def2-TZVP (profiles/r2/class_times_33_*.csv): (dp|ds) -35 %,
+// (ds|dp) -28 %, (dd|ps) -19 %, (fs|pp) -20 %, (fp|ps) -15 %; (ff|ss) +6 %, hence the ket condition.  0 = never.
+#ifndef JQC_BRICK_SPLIT_N
+#define JQC_BRICK_SPLIT_N 90
+#endif
 
 // Per-class layout of the brick kernel, usable at compile time (BrickPlan) and by the host (which
 // classes are supported, how much dynamic shared memory a launch needs).  f32 = the FP32-band
@@ -333,6 +346,7 @@ struct BrickShape {
     int dlk_mode;       // D_lk block (stationary over the brick): 0 registers, 1 lane-private shared memory, 2 reloaded
     int acc_slots, d_slots;   // lane-private doubles (accumulators) and reals (density blocks) per lane
     int regs, minb, nwarps;
+    int isplit;         // passes over the i components (1, or 2 for the largest FP64 blocks)
     size_t rys_bytes, smem;
     bool fits;
 };
@@ -347,6 +361,7 @@ __host__ __device__ constexpr BrickShape brick_shape(int li, int lj, int lk, int
     b.nroots = (li + lj + lk + ll) / 2 + 1;
     b.nwarps = 4;
     b.dlk_mode = b.njkl <= 3 ? 0 : (b.njkl <= 9 ? 1 : 2);
+    b.isplit = (!f32 && JQC_BRICK_SPLIT_N > 0 && b.n >= JQC_BRICK_SPLIT_N && nfi % 2 == 0 && b.njkl > 1) ? 2 : 1;
     if (!f32) {
         const int live = b.n + b.nki + b.njkl;
         b.acc_smem = live > 80 && b.nki > 12;
@@ -383,7 +398,7 @@ struct BrickPlan {
     static constexpr int NKI = B.nki, NJKL = B.njkl, NWARPS = B.nwarps, MINB = B.minb;
     static constexpr int ACC_SLOTS = B.acc_slots, D_SLOTS = B.d_slots;
     static constexpr bool ACC_SMEM = B.acc_smem, DI_SMEM = B.di_smem, FITS = B.fits;
-    static constexpr int DLK_MODE = B.dlk_mode;
+    static constexpr int DLK_MODE = B.dlk_mode, ISPLIT = B.isplit;
     static constexpr size_t SMEM = B.smem, RYS_BYTES = B.rys_bytes;
     // density-block slot offsets (lane-private reals)
     static constexpr int S_DI = 0, S_DLK = DI_SMEM ? NKI : 0;
@@ -395,6 +410,7 @@ struct BrickPlan {
     // Measured (profiles/r2/class_times_21_pipe54.csv): (ss|ss) -15 %, every larger class loses 0-35 %
     // to the extra live registers, hence the threshold of one integral.
     static constexpr bool PIPE = B.n <= JQC_BRICK_PIPE_N;
+    static_assert(!(PIPE && ISPLIT > 1), "the pipelined j loop is for the smallest blocks only");
 };
 
 template <class R> struct BrickRysTab { using type = double2; };
@@ -408,7 +424,7 @@ jk_brick_kernel(const BrickArgs a)
     using P = BrickPlan<R, LI, LJ, LK, LL>;
     using RysT = typename BrickRysTab<R>::type;
     constexpr bool F32 = P::F32;
-    constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL, N = S::N;
+    constexpr int NFI = S::NFI, NFJ = S::NFJ, NFK = S::NFK, NFL = S::NFL;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double2 brick_smem[];
 
@@ -619,20 +635,23 @@ jk_brick_kernel(const BrickArgs a)
                 if (ish == jsh) fac *= R(0.5);
                 if (ksh == lsh) fac *= R(0.5);
                 if (ish == ksh && jsh == lsh) fac *= R(0.5);
-                R eri[N];
+                // evaluate + digest, in P::ISPLIT passes over the i components [IB, IE) (one pass = the whole block)
+                auto pass = [&](auto HC) {
+                constexpr int NIH = NFI / P::ISPLIT, IB = decltype(HC)::value * NIH, IE = IB + NIH;
+                R eri[NIH * NFJ * NFK * NFL];
                 if constexpr (F32)
                     eri_block_regs_f<LI, LJ, LK, LL, P::PIPE>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
                                                               npkl, (float)a.omega, fac, s_rys, kr0, kr1);
                 else
-                    eri_block_regs<LI, LJ, LK, LL, P::PIPE>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
+                    eri_block_regs<LI, LJ, LK, LL, P::PIPE, IB, IE>(eri, a.bra_tab + (size_t)(e - a.j_base) * npij * 8, ket, ri, rj, rk, rl, npij,
                                                             npkl, a.omega, fac, s_rys, kr0, kr1);
-#define ERI_(i, j, k, l) eri[(((i) * NFJ + (j)) * NFK + (k)) * NFL + (l)]
+#define ERI_(i, j, k, l) eri[((((i) - IB) * NFJ + (j)) * NFK + (k)) * NFL + (l)]
                 if constexpr (DO_J) {
                     // J_kl += sum_ij (ij|kl) D[j,i]: lane-stationary
                     R d_ji_l[P::PIPE ? 1 : NFI * NFJ];
                     if constexpr (!P::PIPE) {
 #pragma unroll
-                        for (int i = 0; i < NFI; i++)
+                        for (int i = IB; i < IE; i++)
 #pragma unroll
                         for (int j = 0; j < NFJ; j++) d_ji_l[i * NFJ + j] = ldd((size_t)(j0 + j) * nao + i0 + i);
                     }
@@ -644,23 +663,23 @@ jk_brick_kernel(const BrickArgs a)
                         if constexpr (F32) {
                             R s = R(0);
 #pragma unroll
-                            for (int i = 0; i < NFI; i++)
+                            for (int i = IB; i < IE; i++)
 #pragma unroll
                             for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji_p[i * NFJ + j], s);
                             jkl[k * NFL + l] += (double)s;
                         } else {
                             R s = (R)jkl[k * NFL + l];
 #pragma unroll
-                            for (int i = 0; i < NFI; i++)
+                            for (int i = IB; i < IE; i++)
 #pragma unroll
                             for (int j = 0; j < NFJ; j++) s = fma(ERI_(i, j, k, l), d_ji_p[i * NFJ + j], s);
                             jkl[k * NFL + l] = s;
                         }
                     }
                     // J_ij += sum_kl (ij|kl) D[l,k]: one address for the whole warp -> reduce-scatter
-                    R vij[NFI * NFJ];
+                    R vij[NIH * NFJ];
 #pragma unroll
-                    for (int x = 0; x < NFI * NFJ; x++) vij[x] = R(0);
+                    for (int x = 0; x < NIH * NFJ; x++) vij[x] = R(0);
 #pragma unroll
                     for (int k = 0; k < NFK; k++)
 #pragma unroll
@@ -669,16 +688,16 @@ jk_brick_kernel(const BrickArgs a)
                                   : (P::DLK_MODE == 1 ? DSLOT_(P::S_DLK + k * NFL + l)
                                                       : ldd((size_t)(l0 + l) * nao + k0 + k));
 #pragma unroll
-                        for (int i = 0; i < NFI; i++)
+                        for (int i = IB; i < IE; i++)
 #pragma unroll
-                        for (int j = 0; j < NFJ; j++) vij[i * NFJ + j] = fma(ERI_(i, j, k, l), d, vij[i * NFJ + j]);
+                        for (int j = 0; j < NFJ; j++) vij[(i - IB) * NFJ + j] = fma(ERI_(i, j, k, l), d, vij[(i - IB) * NFJ + j]);
                     }
-                    int idx = 0, cnt = NFI * NFJ;
-                    WarpReduceScatter<NFI * NFJ, 16>::run(vij, lane, idx, cnt);
+                    int idx = 0, cnt = NIH * NFJ;
+                    WarpReduceScatter<NIH * NFJ, 16>::run(vij, lane, idx, cnt);
 #pragma unroll
-                    for (int x = 0; x < warp_rs_final(NFI * NFJ); x++)
+                    for (int x = 0; x < warp_rs_final(NIH * NFJ); x++)
                         if (x < cnt) {
-                            const int i = (idx + x) / NFJ, j = (idx + x) - i * NFJ;
+                            const int ii = (idx + x) / NFJ, j = (idx + x) - ii * NFJ, i = IB + ii;
                             atomicAdd(a.vj + (size_t)(j0 + j) * nao + i0 + i, (double)vij[x]);
                         }
                 }
@@ -693,7 +712,7 @@ jk_brick_kernel(const BrickArgs a)
                         }
                         const R* __restrict__ d = P::PIPE ? d_jl : d_l;
 #pragma unroll
-                        for (int i = 0; i < NFI; i++)
+                        for (int i = IB; i < IE; i++)
 #pragma unroll
                         for (int k = 0; k < NFK; k++) {
                             R s = R(0);
@@ -715,7 +734,7 @@ jk_brick_kernel(const BrickArgs a)
                         }
                         const R* __restrict__ d = P::PIPE ? d_jk : d_l;
 #pragma unroll
-                        for (int i = 0; i < NFI; i++)
+                        for (int i = IB; i < IE; i++)
 #pragma unroll
                         for (int l = 0; l < NFL; l++) {
                             R s = R(0);
@@ -734,7 +753,7 @@ jk_brick_kernel(const BrickArgs a)
                         for (int k = 0; k < NFK; k++) {
                             R s = R(0);
 #pragma unroll
-                            for (int i = 0; i < NFI; i++)
+                            for (int i = IB; i < IE; i++)
 #pragma unroll
                             for (int l = 0; l < NFL; l++) {
                                 const R d = P::DI_SMEM ? DSLOT_(P::S_DI + NFI * NFK + i * NFL + l)
@@ -751,7 +770,7 @@ jk_brick_kernel(const BrickArgs a)
                         for (int l = 0; l < NFL; l++) {
                             R s = R(0);
 #pragma unroll
-                            for (int i = 0; i < NFI; i++)
+                            for (int i = IB; i < IE; i++)
 #pragma unroll
                             for (int k = 0; k < NFK; k++) {
                                 const R d = P::DI_SMEM ? DSLOT_(P::S_DI + i * NFK + k)
@@ -763,6 +782,9 @@ jk_brick_kernel(const BrickArgs a)
                     }
                 }
 #undef ERI_
+                };
+                pass(std::integral_constant<int, 0>{});
+                if constexpr (P::ISPLIT > 1) pass(std::integral_constant<int, 1>{});
             }
             // flush the per-i K accumulators of the lanes that contributed
             if constexpr (DO_K) {

@@ -1,4 +1,4 @@
-# scratch driver for one gpurun call; edited per experiment.  This one: 2 GPUs, shard interleave in alternating direction
+# scratch driver for one gpurun call; edited per experiment.  This one: final state (two-pass brick classes on by default)
 set -x
-python -m pytest tests/test_jk_gpu.py tests/test_nccl_gpu.py -x -q -m gpu -k "shards or nccl or multi_chunk or quartet_list or benzene or loose_cutoff" 2>&1 | tail -3
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_r2_32_2gpu.json 2> gpurun_out/bench_r2_32_2gpu.err; tail -c 400 gpurun_out/bench_r2_32_2gpu.json
+python -m pytest tests -x -q -m gpu > gpurun_out/tests_r2_34.txt 2>&1; tail -n 2 gpurun_out/tests_r2_34.txt
+python bench.py --steps 1 --warmup 1 --no-extras --no-cpu-baseline --class-profile gpurun_out/class_times_r2_34.csv > gpurun_out/bench_r2_34.json 2> gpurun_out/bench_r2_34.err; head -c 300 gpurun_out/bench_r2_34.json
