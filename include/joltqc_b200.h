@@ -88,7 +88,8 @@ int jqc_dm_to_mol(jqc_engine* eng, const double* kern_dev, int n, double* mol_de
  * (jk.py:93-96; selection rule screen_jk_tasks.cu:258-261): quartets with estimate above
  * cutoff_fp32 are evaluated; those not above cutoff_fp64 form the FP32 band and are evaluated in
  * single precision with FP64 accumulation (jk.py:241-328) for the angular classes that have an FP32
- * kernel (integral blocks <= 108 elements, one density matrix, hermi == 1), in FP64 otherwise.  With
+ * kernel (every class up to f shells, and g-shell classes with blocks <= 108 elements; one density
+ * matrix, hermi == 1), in FP64 otherwise.  With
  * cutoff_fp64 <= cutoff_fp32 (the default 1e-13 / 1e-13) the build is FP64 only.
  * Work is enqueued on `stream` (cudaStream_t, NULL = default stream); the call performs one host
  * synchronisation before the heavy kernels are enqueued (active tile counts), none afterwards;
