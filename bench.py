@@ -528,20 +528,31 @@ def main():
     }
     if per_rank is not None:
         line["per_rank"] = per_rank
+    # Auxiliary legs (comparisons beside the headline, all outside the timed region): a failure in one of them
+    # is recorded in the line instead of losing the measurement above.
+    def leg(name, fn):
+        try:
+            line[name] = fn()
+        except Exception as exc:                       # noqa: BLE001 - reported, not swallowed
+            line[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            print("bench.py: leg %r failed: %r" % (name, exc), file=sys.stderr)
+
     if world == 1:
-        line["mixed_precision"] = mixed_leg(eng, dm_dev, vj, vk)
+        leg("mixed_precision", lambda: mixed_leg(eng, dm_dev, vj, vk))
     if world == 1 and not args.no_extras:
-        line["ref_kernels"] = ref_kernels_leg(lay, eng, dm_dev)
+        leg("ref_kernels", lambda: ref_kernels_leg(lay, eng, dm_dev))
         if "value" in line["ref_kernels"]:
             line["ref_kernels"]["speedup_of_this_engine"] = line["ref_kernels"]["value"] / (ms * 1e-3)
-        line["extra"] = extra_configs(peak_probe, dev)
+        leg("extra", lambda: extra_configs(peak_probe, dev))
     if not args.no_cpu_baseline and world == 1:
-        res = cpu_port_baseline(lay, dm)
-        est = res["seconds_sample"] * res["stride"]
-        line["cpu_baseline"] = {"value": est, "unit": "s/iter", "cores": res["cores"], "kind": "port",
-                                "sample": f"every {res['stride']}th (ij) shell pair of the same build "
-                                          f"({res['quartets_sample']} quartets in {res['seconds_sample']:.2f} s), extrapolated x{res['stride']}",
-                                "anchor": cpu_anchor()}
+        def cpu_leg():
+            res = cpu_port_baseline(lay, dm)
+            est = res["seconds_sample"] * res["stride"]
+            return {"value": est, "unit": "s/iter", "cores": res["cores"], "kind": "port",
+                    "sample": f"every {res['stride']}th (ij) shell pair of the same build "
+                              f"({res['quartets_sample']} quartets in {res['seconds_sample']:.2f} s), extrapolated x{res['stride']}",
+                    "anchor": cpu_anchor()}
+        leg("cpu_baseline", cpu_leg)
     _emit(line)
     if dist is not None:
         dist.barrier()
