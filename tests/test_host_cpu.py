@@ -145,3 +145,35 @@ def test_apply_keeps_reference_surface():
     assert list(sig.parameters) == ["basis_layout", "cutoff_fp64", "cutoff_fp32"]
     for name in ("generate_get_j", "generate_get_k", "generate_get_jk", "generate_get_veff"):
         assert hasattr(jk, name)
+
+
+def test_jk_pair_surface(monkeypatch):
+    """joltqc_b200.pyscf.jk_pair mirrors jqc/pyscf/jk_pair.py:49-115 (names, argument order incl. pair_wide_vk)
+    and hands the cutoffs to the same engine-backed generator."""
+    import inspect
+    from joltqc_b200.pyscf import jk, jk_pair
+    seen = []
+    monkeypatch.setattr(jk, "generate_jk_kernel",
+                        lambda lay, cutoff_fp64=1e-13, cutoff_fp32=1e-13: seen.append((lay, cutoff_fp64, cutoff_fp32)) or
+                        (lambda *a, **k: (("J", k), ("K", k))))
+    for name in ("generate_get_j", "generate_get_k", "generate_get_jk", "generate_jk_kernel"):
+        sig = inspect.signature(getattr(jk_pair, name))
+        assert list(sig.parameters) == ["basis_layout", "cutoff_fp64", "cutoff_fp32", "pair_wide_vk"]
+    assert jk_pair.generate_get_j("L", 1e-7, 1e-13, pair_wide_vk=32)("mol", "dm", hermi=1)[0] == "J"
+    assert jk_pair.generate_get_k("L", cutoff_fp64=1e-9)("mol", "dm")[1]["with_k"] is True
+    assert seen == [("L", 1e-7, 1e-13), ("L", 1e-9, 1e-13)]
+
+
+def test_shard_entry_partition(tmp_path):
+    """The static multi-GPU partition (shard_entry, jqc_common.cuh) hands every task to exactly one rank."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "shard_entry_check")
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-I", os.path.join(root, "joltqc_b200", "csrc"),
+                    os.path.join(root, "tests", "shard_entry_check.cu"), "-o", exe], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "OK", out.stdout + out.stderr
