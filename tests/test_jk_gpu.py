@@ -337,3 +337,18 @@ def test_multilane_kernel_variants(torch_cuda, monkeypatch, mode):
     orc.get_jk(random_dm(lay._mol.nao, 9) / 264, 1)
     assert np.array_equal(counts, orc.last_counts)
     _fresh_check(monkeypatch, {"JQC_BWARP": mode}, H2O, "def2-tzvpp", omega=0.3)
+
+
+def test_engine_matches_golden_fixture(torch_cuda):
+    """The CUDA engine against the committed golden J/K vectors (tests/golden/jk_small_cases.npz) — the same
+    comparison as the oracle tests above, but with nothing of oracle/ executed."""
+    import os
+    from joltqc_b200.pyscf.jk import generate_jk_kernel
+    from tests.golden.make_jk_golden import CASES
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "jk_small_cases.npz"))
+    for name, (atom, basis, cart, unit, seed, hermi, omega) in CASES.items():
+        mol, lay = make(atom, basis, cart=cart, unit=unit)
+        vj, vk = generate_jk_kernel(lay)(mol, g[name + "_dm"], hermi=hermi, omega=omega)
+        rj, rk = g[name + "_vj"], g[name + "_vk"]
+        assert np.abs(vj.cpu().numpy() - rj).max() < TOL * max(1.0, np.abs(rj).max()), name
+        assert np.abs(vk.cpu().numpy() - rk).max() < TOL * max(1.0, np.abs(rk).max()), name

@@ -122,3 +122,18 @@ def test_reference_golden_rhf_energy(cart, e_ref):
     e = mf.kernel()
     assert mf.converged
     assert abs(e - e_ref) < 1e-9, e - e_ref
+
+
+def test_oracle_reproduces_golden_jk_fixture():
+    """tests/golden/jk_small_cases.npz (frozen by tests/golden/make_jk_golden.py): the oracle of today reproduces the
+    committed J/K vectors — a regression pin for the checker itself."""
+    import os
+    from oracle.oracle import OracleJK
+    from tests.golden.make_jk_golden import CASES
+    from tests.common import make
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "jk_small_cases.npz"))
+    for name, (atom, basis, cart, unit, seed, hermi, omega) in CASES.items():
+        mol, lay = make(atom, basis, cart=cart, unit=unit)
+        vj, vk = OracleJK(lay).get_jk(g[name + "_dm"], hermi, True, True, omega, 1e-13)
+        assert np.abs(vj - g[name + "_vj"]).max() < 1e-11 * np.abs(vj).max(), name
+        assert np.abs(vk - g[name + "_vk"]).max() < 1e-11 * np.abs(vk).max(), name
